@@ -1,0 +1,239 @@
+"""Generates tests/golden/*.npz FROM THE REFERENCE'S OWN FILES and pins the oracle to them.
+
+Run here (this container has /root/reference; the GPU box does not):
+    python tests/golden/make_golden.py
+
+What it does
+  1. env_kat.npz     the reference's classic_control env classes (imported unmodified through
+                     oracle/ref_loader.py) are stepped with deterministic fp32 actions
+                     a_t[d] = A*sin(0.05 t + d); per-step obs / reward / termination are stored
+                     together with the sampled contexts (reset(seed)).
+  2. bb_*.npz        the reference's own BlackBoxWrapper.step loop + controllers + TimeLimit
+                     semantics + TimeAwareObservation, driven by the oracle's 'shipped' MP
+                     restatement (mp_pytorch itself is absent: see oracle/mp.py header), for the
+                     three BASELINE envs incl. replanning / condition_on_desired.
+  3. asserts that oracle/reacher.py and oracle/blackbox.py reproduce every stored array
+     (bit-exact for obs/flags/lengths, <= 4e-16 relative for float64 rewards: numpy's 1-D
+     `linalg.norm` and the batched sqrt(dx^2+dy^2) may differ by one ulp).
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import mp as omp  # noqa: E402
+from oracle import ref_loader as rl  # noqa: E402
+from oracle.blackbox import RESOLVED, make_oracle  # noqa: E402
+from oracle.reacher import BatchedReacher  # noqa: E402
+
+ENV_CASES = [
+    # name, oracle kind, oracle kwargs, seeds, amplitudes
+    ("HoleReacher-v0", "hole", dict(n_links=5, random_start=True, hole_width=None, hole_depth=1, hole_x=None,
+                                    collision_penalty=100), [0, 1, 2, 3, 4, 5, 6, 7], [0.3, 1.5, 6.0, 3.0, 0.1, 2.0, 4.0, 1.0]),
+    ("ViaPointReacher-v0", "viapoint", dict(n_links=5, collision_penalty=1000), [0, 1, 2, 3], [0.3, 6.0, 1.5, 3.0]),
+    ("SimpleReacher-v0", "simple", dict(n_links=2), [0, 1, 2, 3], [5.0, 20.0, 100.0, 1.0]),
+    ("LongSimpleReacher-v0", "simple", dict(n_links=5), [0, 1], [5.0, 50.0]),
+]
+
+
+def close64(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    same_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    with np.errstate(invalid="ignore"):
+        ok = same_inf | (np.abs(a - b) <= 4e-16 * np.maximum(np.abs(a), np.abs(b)))
+    return bool(np.all(ok))
+
+
+def gen_env_kat(ns):
+    out = {}
+    for name, kind, kw, seeds, amps in ENV_CASES:
+        n = kw["n_links"]
+        T = 200
+        obs_dim = None
+        rec = dict(obs0=[], obs=[], rew=[], term=[], length=[])
+        ctx_rec = []
+        for s, A in zip(seeds, amps):
+            env = rl.make_step_env(ns, name)
+            ob0, _ = env.reset(seed=s)
+            obs_dim = ob0.shape[0]
+            obs = np.zeros((T, obs_dim), np.float32)
+            rew = np.zeros(T)
+            term = np.zeros(T, bool)
+            L = T
+            for t in range(T):
+                a = (A * np.sin(0.05 * t + np.arange(n))).astype(np.float32)
+                ob, r, te, tr, info = env.step(a)
+                obs[t], rew[t], term[t] = ob, r, te
+                if te:
+                    L = t + 1
+                    break
+            rec["obs0"].append(ob0); rec["obs"].append(obs); rec["rew"].append(rew)
+            rec["term"].append(term); rec["length"].append(L)
+            if kind == "hole":
+                ctx_rec.append([env._tmp_x, env._tmp_width, float(env._tmp_depth), env._start_pos[0]])
+            elif kind == "viapoint":
+                ctx_rec.append([*env._via_point, *env._goal, env._start_pos[0]])
+            else:
+                ctx_rec.append([*env._goal, env._start_pos[0]])
+        key = name.replace("-", "_")
+        out[f"{key}/seeds"] = np.array(seeds)
+        out[f"{key}/amps"] = np.array(amps)
+        out[f"{key}/ctx"] = np.array(ctx_rec, dtype=np.float64)
+        for k, v in rec.items():
+            out[f"{key}/{k}"] = np.stack(v) if k != "length" else np.array(v)
+
+        # ---- pin the oracle ----
+        o = BatchedReacher(kind, **kw)
+        ob0 = o.reset(seeds=seeds)
+        assert np.array_equal(ob0, out[f"{key}/obs0"]), name
+        for t in range(T):
+            a = np.stack([(A * np.sin(0.05 * t + np.arange(n))).astype(np.float32) for A in amps])
+            ob, r, te, info = o.step(a)
+            for i in range(len(seeds)):
+                if t < out[f"{key}/length"][i]:
+                    assert np.array_equal(ob[i], out[f"{key}/obs"][i, t]), (name, i, t)
+                    assert close64(r[i], out[f"{key}/rew"][i, t]), (name, i, t, r[i], out[f"{key}/rew"][i, t])
+                    assert te[i] == out[f"{key}/term"][i, t], (name, i, t)
+        print(f"env_kat {name}: oracle == reference files on {len(seeds)} seeds, lengths {out[f'{key}/length']}")
+    np.savez_compressed(os.path.join(HERE, "env_kat.npz"), **out)
+
+
+class TorchTrajGen:
+    """Adapts an oracle.mp generator to the torch-tensor interface BlackBoxWrapper calls
+    (black_box_wrapper.py:57,62-65,102,106,113-118,124,226)."""
+
+    def __init__(self, tg):
+        import torch
+        self.torch = torch
+        self.tg = tg
+        self.phase_gn = tg.phase_gn
+
+    def set_duration(self, duration, dt):
+        self.tg.set_duration(duration, dt)
+
+    def set_params(self, p):
+        self.tg.set_params(np.asarray(p))
+
+    def set_initial_conditions(self, t, pos, vel):
+        self.tg.set_initial_conditions(t, pos, vel)
+
+    def get_traj_pos(self):
+        return self.torch.from_numpy(np.ascontiguousarray(self.tg.get_traj_pos()))
+
+    def get_traj_vel(self):
+        return self.torch.from_numpy(np.ascontiguousarray(self.tg.get_traj_vel()))
+
+    def get_params_bounds(self):
+        return self.torch.from_numpy(self.tg.get_params_bounds())
+
+    def reset(self):
+        self.tg.reset()
+
+
+def build_reference_bb(ns, env_id, mode, bb_kwargs):
+    """reference BlackBoxWrapper(MPWrapper([TimeAwareObservation](TimeLimit(env)))) as make_bb
+    (utils/make_env_helpers.py:68-136) would assemble it, with the oracle MP as traj_gen."""
+    cfg = RESOLVED[env_id]
+    name = env_id.split("/")[1]
+    env = ns.TimeLimit(rl.make_step_env(ns, name), 200)
+    if bb_kwargs.get("replanning_schedule") or bb_kwargs.get("learn_sub_trajectories"):
+        taw = importlib.import_module("fancy_gym.utils.wrappers").TimeAwareObservation
+        env = taw(env)
+    wrap = {"HoleReacher-v0": ns.MPWrapper_HoleReacher, "ViaPointReacher-v0": ns.MPWrapper_ViaPoint,
+            "SimpleReacher-v0": ns.MPWrapper_SimpleReacher}[name]
+    env = wrap(env)
+    orc = make_oracle(env_id, mode=mode, **bb_kwargs)       # only to get an identically configured traj_gen
+    ctrl = ns.get_controller(**cfg["ctrl"])
+    return ns.BlackBoxWrapper(env, TorchTrajGen(orc.traj_gen), ctrl, duration=2.0, verbose=2, **bb_kwargs)
+
+
+def params_for(env_id, seed, n_plans):
+    P = {"fancy_ProMP/HoleReacher-v0": 25, "fancy_DMP/ViaPointReacher-v0": 30, "fancy_ProDMP/SimpleReacher-v0": 12}[env_id]
+    rng = np.random.default_rng(1234 + seed)
+    return (0.5 * rng.standard_normal((n_plans, P))).astype(np.float32)
+
+
+BB_CASES = [
+    ("bb_holereacher_promp", "fancy_ProMP/HoleReacher-v0", list(range(32)), {}),
+    ("bb_viapoint_dmp", "fancy_DMP/ViaPointReacher-v0", list(range(8)), {}),
+    ("bb_simplereacher_prodmp", "fancy_ProDMP/SimpleReacher-v0", list(range(8)), {}),
+    ("bb_simplereacher_prodmp_replan", "fancy_ProDMP/SimpleReacher-v0", list(range(8)),
+     dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4, condition_on_desired=False)),
+    ("bb_simplereacher_prodmp_replan_cod", "fancy_ProDMP/SimpleReacher-v0", list(range(8)),
+     dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4, condition_on_desired=True)),
+    ("bb_holereacher_promp_replan", "fancy_ProMP/HoleReacher-v0", list(range(8)),
+     dict(replanning_schedule=lambda p, v, o, a, t: t % 50 == 0)),
+]
+
+
+def gen_bb(ns):
+    for fname, env_id, seeds, bbk in BB_CASES:
+        n_plans = 8 if bbk.get("replanning_schedule") else 1
+        rec = {k: [] for k in ("obs0", "params", "positions", "velocities", "step_obs", "step_rewards",
+                               "ret", "length", "terminated", "truncated", "obs", "n_calls")}
+        for s in seeds:
+            bb = build_reference_bb(ns, env_id, "shipped", bbk)
+            ob0, _ = bb.reset(seed=s)
+            th = params_for(env_id, s, n_plans)
+            per = {k: [] for k in rec if k not in ("obs0", "params", "n_calls")}
+            calls = 0
+            for i in range(n_plans):
+                ob, ret, te, tr, info = bb.step(th[i])
+                calls += 1
+                L = info["trajectory_length"]
+                T = info["positions"].shape[0]
+                so = np.zeros((T, info["step_observations"].shape[1]), np.float32)
+                so[:L] = info["step_observations"]
+                sr = np.zeros(T)
+                sr[:L] = info["step_rewards"]
+                for k, v in (("positions", info["positions"]), ("velocities", info["velocities"]), ("step_obs", so),
+                             ("step_rewards", sr), ("ret", ret), ("length", L), ("terminated", te),
+                             ("truncated", tr), ("obs", ob)):
+                    per[k].append(np.asarray(v))
+                if te or tr:
+                    break
+            # pad to n_plans calls
+            while len(per["ret"]) < n_plans:
+                for k in per:
+                    per[k].append(np.zeros_like(per[k][0]))
+            rec["obs0"].append(ob0); rec["params"].append(th); rec["n_calls"].append(calls)
+            for k in per:
+                rec[k].append(np.stack(per[k]))
+        out = {k: np.stack(v) for k, v in rec.items()}
+        out["seeds"] = np.array(seeds)
+        np.savez_compressed(os.path.join(HERE, fname + ".npz"), **out)
+
+        # ---- pin the oracle's loop (same 'shipped' MP) against the reference's BlackBoxWrapper ----
+        orc = make_oracle(env_id, mode="shipped", verbose=2, **bbk)
+        ob0 = orc.reset(seeds=seeds)
+        assert np.array_equal(ob0, out["obs0"]), fname
+        alive = np.ones(len(seeds), bool)
+        for i in range(n_plans):
+            ob, ret, te, tr, info = orc.step(out["params"][:, i])
+            for b in range(len(seeds)):
+                if i >= out["n_calls"][b]:
+                    continue
+                L = out["length"][b, i]
+                assert info["trajectory_length"][b] == L, (fname, b, i, info["trajectory_length"][b], L)
+                assert np.array_equal(info["positions"][b], out["positions"][b, i]), (fname, b, i)
+                assert np.array_equal(info["velocities"][b], out["velocities"][b, i]), (fname, b, i)
+                assert np.array_equal(info["step_observations"][b, :L], out["step_obs"][b, i, :L]), (fname, b, i)
+                assert close64(info["step_rewards"][b, :L], out["step_rewards"][b, i, :L]), (fname, b, i)
+                assert close64(ret[b], out["ret"][b, i]), (fname, b, i, ret[b], out["ret"][b, i])
+                assert te[b] == out["terminated"][b, i] and tr[b] == out["truncated"][b, i], (fname, b, i)
+                assert np.array_equal(ob[b], out["obs"][b, i]), (fname, b, i)
+        print(f"{fname}: oracle loop == reference BlackBoxWrapper on {len(seeds)} seeds; calls {out['n_calls']}, "
+              f"lengths[0] {out['length'][0]}")
+
+
+if __name__ == "__main__":
+    assert rl.available(), "needs /root/reference"
+    ns = rl.load()
+    gen_env_kat(ns)
+    gen_bb(ns)
+    print("golden vectors written to", HERE)
