@@ -1,0 +1,353 @@
+"""Batched black-box (episode-based) environment: the vectorised twin of
+fancy_gym/black_box/black_box_wrapper.py.
+
+step(params[B, P]) -> (obs[B, O], return[B], terminated[B], truncated[B], infos) runs, for all B
+envs, trajectory generation + tracking controller + clip + env dynamics + reward aggregation as
+ONE fused CUDA kernel launch (fg_rollout).  The Python side only keeps the bookkeeping of the
+reference wrapper (plan counters, replanning schedule, finalised tau/delay, condition_on_desired)
+and builds / caches the per-plan kernel handle.  There is no CPU fallback.
+
+With num_envs == 1 and a 1-D numpy action the call returns the reference's scalar contract:
+(obs[O] ndarray, float, bool, bool, dict).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..mp import MPInterface
+from ..utils.gym_compat import Box, Wrapper
+from .controller import BaseController, PDController, PosController, VelController
+from .raw_interface_wrapper import RawInterfaceWrapper
+
+_CTRL_KIND = {"velocity": _lib.CTRL_VELOCITY, "position": _lib.CTRL_POSITION, "motor": _lib.CTRL_MOTOR}
+
+
+class BlackBoxWrapper(Wrapper):
+
+    def __init__(self,
+                 env: RawInterfaceWrapper,
+                 trajectory_generator: MPInterface,
+                 tracking_controller: BaseController,
+                 duration: float,
+                 verbose: int = 1,
+                 learn_sub_trajectories: bool = False,
+                 replanning_schedule: Optional[Callable] = None,
+                 reward_aggregation: Callable[[np.ndarray], float] = np.sum,
+                 max_planning_times: int = np.inf,
+                 condition_on_desired: bool = False,
+                 wall_mode: int = 0):
+        super().__init__(env)
+        self.duration = duration
+        self.learn_sub_trajectories = learn_sub_trajectories
+        self.do_replanning = replanning_schedule is not None
+        self.replanning_schedule = replanning_schedule or (lambda *x: False)
+        self.current_traj_steps = 0
+
+        self.traj_gen = trajectory_generator
+        self.tracking_controller = tracking_controller
+        self.traj_gen.set_duration(self.duration, self.dt)
+
+        self.tau_bound = [-np.inf, np.inf]
+        self.delay_bound = [-np.inf, np.inf]
+        if hasattr(self.traj_gen.phase_gn, "tau_bound"):
+            self.tau_bound = self.traj_gen.phase_gn.tau_bound
+        if hasattr(self.traj_gen.phase_gn, "delay_bound"):
+            self.delay_bound = self.traj_gen.phase_gn.delay_bound
+
+        self.reward_aggregation = reward_aggregation
+        self.return_context_observation = not (learn_sub_trajectories or self.do_replanning)
+        self.traj_gen_action_space = self._get_traj_gen_action_space()
+        self.action_space = self._get_action_space()
+        self.observation_space = self._get_observation_space()
+
+        self.do_render = False
+        self.verbose = verbose
+        self.condition_on_desired = condition_on_desired
+        self.condition_set = False
+        self.max_planning_times = max_planning_times
+        self.plan_steps = 0
+        self.wall_mode = int(wall_mode)
+
+        # ---- device side ----
+        base = self.env.unwrapped
+        self._base = base
+        self.num_envs = base.num_envs
+        self.device = base.device
+        self.traj_gen.device = self.device
+        B, n = self.num_envs, base.n_links
+        dev = self.device
+        self._ret = torch.zeros(B, dtype=torch.float64, device=dev)
+        self._len = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._flags = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._info = torch.zeros(B, 4, dtype=torch.float64, device=dev)
+        self._cond_pos = torch.zeros(B, n, dtype=torch.float32, device=dev)
+        self._cond_vel = torch.zeros(B, n, dtype=torch.float32, device=dev)
+        self._obs = None
+        self._handles: Dict[Any, C.c_void_p] = {}
+        self._lo = torch.as_tensor(self.traj_gen_action_space.low, device=dev)
+        self._hi = torch.as_tensor(self.traj_gen_action_space.high, device=dev)
+        self._has_finite_bounds = bool(np.isfinite(self.traj_gen_action_space.low).any()
+                                       or np.isfinite(self.traj_gen_action_space.high).any())
+
+    # ---- spaces (black_box_wrapper.py:122-148) --------------------------------------------------
+    def _get_traj_gen_action_space(self):
+        lo, hi = self.traj_gen.get_params_bounds()
+        return Box(low=lo.numpy(), high=hi.numpy(), dtype=self.env.action_space.dtype,
+                   batch=self.env.unwrapped.num_envs if self.env.unwrapped.num_envs > 1 else None)
+
+    def _get_action_space(self):
+        return self.traj_gen_action_space
+
+    def _time_aware(self) -> bool:
+        return bool(getattr(self.env, "time_aware", False))
+
+    def _obs_index(self):
+        full = self.env.observation_space.shape[0]
+        if self.return_context_observation:
+            return np.nonzero(np.asarray(self.env.context_mask, dtype=bool))[0]
+        return np.arange(full)
+
+    def _get_observation_space(self):
+        space = self.env.observation_space
+        if self.return_context_observation:
+            mask = np.asarray(self.env.context_mask, dtype=bool)
+            return Box(low=space.low[mask], high=space.high[mask], dtype=space.dtype, batch=space.batch)
+        return space
+
+    def observation(self, observation):
+        if self.return_context_observation:
+            observation = observation[..., torch.as_tensor(self._obs_index(), device=observation.device)]
+        return observation.to(torch.float32)
+
+    # ---- kernel handle for the current plan -----------------------------------------------------
+    def _controller_cfg(self, cfg):
+        ctrl = self.tracking_controller
+        kind = getattr(ctrl, "kind", None)
+        if kind not in _CTRL_KIND:
+            raise NotImplementedError(f"controller {type(ctrl).__name__} is not available inside the fused kernel")
+        cfg.ctrl_kind = _CTRL_KIND[kind]
+        n = self._base.n_links
+        p = np.broadcast_to(np.asarray(getattr(ctrl, "p_gains", 0.0), dtype=np.float64), (n,))
+        d = np.broadcast_to(np.asarray(getattr(ctrl, "d_gains", 0.0), dtype=np.float64), (n,))
+        for i in range(n):
+            cfg.p_gains[i], cfg.d_gains[i] = float(p[i]), float(d[i])
+
+    def _handle(self):
+        tg, base = self.traj_gen, self._base
+        key = tg.table_key()
+        h = self._handles.get(key)
+        if h is not None:
+            return h
+        tb = tg.tables()
+        cfg = _lib.FgConfig()
+        cfg.struct_size = C.sizeof(_lib.FgConfig)
+        cfg.env_kind, cfg.mp_kind = base.env_kind, tb.mp_kind
+        self._controller_cfg(cfg)
+        cfg.n_dof, cfg.n_steps, cfg.n_basis = base.n_links, tb.n_steps, tb.n_basis
+        cfg.max_episode_steps = int(self.env.spec.max_episode_steps)
+        cfg.dt = float(self.dt)
+        cfg.tau, cfg.dmp_alpha = tb.tau, tb.dmp_alpha
+        cfg.weights_scale, cfg.goal_scale, cfg.relative_goal = tb.weights_scale, tb.goal_scale, tb.relative_goal
+        cfg.allow_self_collision = int(bool(getattr(base, "allow_self_collision", False)))
+        cfg.allow_wall_collision = int(bool(getattr(base, "allow_wall_collision", False)))
+        cfg.collision_penalty = float(getattr(base, "collision_penalty", 0.0))
+        cfg.rew_fct = 0
+        cfg.wall_mode = self.wall_mode
+        cfg.time_aware = int(self._time_aware())
+        idx = self._obs_index()
+        cfg.n_obs_out = len(idx)
+        for j, i in enumerate(idx):
+            cfg.obs_index[j] = int(i)
+        ta = np.ascontiguousarray(tb.tab_a, dtype=np.float32)
+        tbb = np.ascontiguousarray(tb.tab_b, dtype=np.float32)
+        cfg.tab_a, cfg.tab_b = ta.ctypes.data, tbb.ctypes.data
+        hp = C.c_void_p()
+        _lib.check(_lib.lib.fg_create(C.byref(cfg), self.device.index or 0, C.byref(hp)))
+        self._handles[key] = hp
+        return hp
+
+    # ---- replanning: how many steps does this plan execute? (black_box_wrapper.py:197) -----------
+    def _segment_steps(self, n_steps: int):
+        """The schedule is evaluated on the host with the step counter only — every schedule in the
+        reference and its tests has the form `t % k == 0`.  A schedule that inspects pos / vel / obs /
+        action cannot be fused and raises."""
+        if not self.do_replanning or not (self.plan_steps < self.max_planning_times):
+            return n_steps, False
+        for t in range(n_steps):
+            try:
+                fire = self.replanning_schedule(None, None, None, None, t + 1 + self.current_traj_steps)
+            except TypeError as e:
+                raise NotImplementedError("replanning_schedule must depend on the step counter only "
+                                          "(it is evaluated on the host, outside the fused kernel)") from e
+            if fire:
+                return t + 1, True
+        return n_steps, False
+
+    # ---- the hot path ---------------------------------------------------------------------------
+    def get_trajectory(self, action):
+        """black_box_wrapper.py:96-120 — stand-alone trajectory (fg_trajgen); the fused step does not call this."""
+        params = self._prepare_params(action)[0]
+        self._set_plan(params)
+        if self.condition_set:
+            self.traj_gen.set_initial_conditions(self.traj_gen.init_time, self._cond_pos, self._cond_vel)
+        return self.traj_gen.get_traj_pos(), self.traj_gen.get_traj_vel()
+
+    def _prepare_params(self, action):
+        as_numpy = not torch.is_tensor(action)
+        a = torch.as_tensor(np.asarray(action)) if as_numpy else action
+        scalar = a.dim() == 1
+        if scalar:
+            if self.num_envs != 1:
+                raise ValueError(f"expected params of shape [{self.num_envs}, {self.action_space.shape[0]}]")
+            a = a[None]
+        if a.shape != (self.num_envs, self.action_space.shape[0]):
+            raise ValueError(f"expected params of shape [{self.num_envs}, {self.action_space.shape[0]}], got {tuple(a.shape)}")
+        a = a.to(self.device, torch.float32, non_blocking=True)
+        if self._has_finite_bounds:
+            a = torch.minimum(torch.maximum(a, self._lo), self._hi)     # np.clip to the tau / delay bounds (:104-105)
+        return a.contiguous(), as_numpy, scalar
+
+    def _set_plan(self, params):
+        tg = self.traj_gen
+        duration = self.duration
+        if self.learn_sub_trajectories:
+            duration = None
+            tg.reset()
+        tg.set_params(params)
+        init_time = 0 if not self.do_replanning else self.current_traj_steps * self.dt
+        tg.set_initial_conditions(init_time, self._base.q, self._base.v)   # current_pos / current_vel (:110-111)
+        tg.set_duration(duration, self.dt)
+
+    def step(self, action):
+        base = self._base
+        params, as_numpy, scalar = self._prepare_params(action)
+        self._set_plan(params)
+        local = self.traj_gen.params.contiguous()
+        T = self.traj_gen.n_steps
+        self.plan_steps += 1
+        seg, replan_break = self._segment_steps(T)
+        h = self._handle()
+
+        B, n = self.num_envs, base.n_links
+        if self._obs is None or self._obs.shape[1] != len(self._obs_index()):
+            self._obs = torch.zeros(B, len(self._obs_index()), dtype=torch.float32, device=self.device)
+        io = _lib.FgRolloutIO()
+        io.struct_size = C.sizeof(_lib.FgRolloutIO)
+        io.params = local.data_ptr()
+        io.ctx = base.ctx.data_ptr()
+        io.q, io.v, io.steps, io.done = base.q.data_ptr(), base.v.data_ptr(), base.steps.data_ptr(), base.done.data_ptr()
+        io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
+        io.use_cond = int(self.condition_set)
+        io.write_cond = (2 if replan_break else 1) if self.condition_on_desired else 0
+        io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
+        io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
+        dbg = None
+        need_rewards = self.verbose >= 2 or self.reward_aggregation not in (np.sum, np.mean, sum)
+        if need_rewards:
+            dbg = dict(rewards=torch.zeros(B, T, dtype=torch.float64, device=self.device))
+            io.dbg_rewards = dbg["rewards"].data_ptr()
+            if self.verbose >= 2:
+                dbg["actions"] = torch.zeros(B, T, n, dtype=torch.float64, device=self.device)
+                io.dbg_actions = dbg["actions"].data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(seg), C.c_void_p(stream)))
+        if self.condition_on_desired:
+            self.condition_set = True      # every live env breaks at the same step or is done
+
+        self.current_traj_steps += seg     # live envs all advance by `seg`; finished envs are frozen
+        length = self._len.clone()
+        flags = self._flags
+        terminated = (flags & _lib.FLAG_TERMINATED) != 0
+        truncated = (flags & _lib.FLAG_TRUNCATED) != 0
+        ret = self._ret.clone()
+        if self.reward_aggregation is np.mean:
+            ret = ret / length.clamp(min=1)
+        infos: Dict[str, Any] = {}
+        if base.env_kind in (_lib.ENV_HOLE_REACHER, _lib.ENV_VIAPOINT_REACHER):
+            infos["is_success"] = (flags & _lib.FLAG_SUCCESS) != 0
+            infos["is_collided"] = (flags & _lib.FLAG_COLLIDED) != 0
+            infos["end_effector"] = self._info[:, 0:2].clone()
+        elif base.env_kind == _lib.ENV_SIMPLE_REACHER:
+            infos["reward_dist"] = self._info[:, 0].clone()
+            infos["reward_ctrl"] = self._info[:, 1].clone()
+        if need_rewards and self.reward_aggregation not in (np.sum, np.mean, sum):
+            r = dbg["rewards"].cpu().numpy()
+            ln = length.cpu().numpy()
+            ret = torch.as_tensor(np.array([self.reward_aggregation(r[b, :ln[b]]) if ln[b] else 0.0 for b in range(B)]),
+                                  device=self.device)
+        if self.verbose >= 2:
+            pos, vel = self._planned_trajectory(local)
+            infos["positions"], infos["velocities"] = pos, vel
+            infos["step_actions"] = dbg["actions"]
+            infos["step_rewards"] = dbg["rewards"]
+        infos["trajectory_length"] = length
+        obs = self._obs.clone()
+        return self._format(obs, ret, terminated, truncated, infos, as_numpy, scalar)
+
+    def _planned_trajectory(self, local_params):
+        tg = self.traj_gen
+        saved = tg.params
+        tg.params = local_params
+        if self.condition_set and self.plan_steps > 1:
+            tg.set_initial_conditions(tg.init_time, self._cond_pos, self._cond_vel)
+        pos, vel = tg.get_traj_pos(), tg.get_traj_vel()
+        tg.params = saved
+        return pos, vel
+
+    def _format(self, obs, ret, terminated, truncated, infos, as_numpy, scalar):
+        if not as_numpy:
+            return obs, ret, terminated, truncated, infos
+
+        def host(x):
+            return x.cpu().numpy() if torch.is_tensor(x) else x
+        obs, ret, terminated, truncated = host(obs), host(ret), host(terminated), host(truncated)
+        infos = {k: host(v) for k, v in infos.items()}
+        if scalar:
+            L = int(infos["trajectory_length"][0])
+            out = {}
+            for k, v in infos.items():
+                v0 = v[0]
+                if k in ("step_actions", "step_rewards", "step_observations"):
+                    v0 = v0[:L]
+                elif k == "trajectory_length":
+                    v0 = L
+                elif np.ndim(v0) == 0:
+                    v0 = v0.item()
+                out[k] = v0
+            return obs[0], float(ret[0]), bool(terminated[0]), bool(truncated[0]), out
+        return obs, ret, terminated, truncated, infos
+
+    def render(self):
+        self.do_render = True
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[Dict[str, Any]] = None):
+        """black_box_wrapper.py:222-229"""
+        self.current_traj_steps = 0
+        self.plan_steps = 0
+        self.traj_gen.reset()
+        self.condition_set = False
+        obs, info = self.env.reset(seed=seed, options=options)
+        obs = self.observation(obs)
+        self._obs = obs.clone().contiguous()
+        as_numpy = (options or {}).get("as_numpy", self.num_envs == 1)
+        if as_numpy:
+            obs = obs.cpu().numpy()
+            if self.num_envs == 1:
+                obs = obs[0]
+        return obs, info
+
+    def close(self):
+        for h in self._handles.values():
+            _lib.lib.fg_destroy(h)
+        self._handles.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,210 @@
+// C ABI of fancy_gym_b200 (include/fancy_gym_b200.h): handle management and kernel dispatch.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "fancy_gym_b200.h"
+#include "fg_device.cuh"
+#include "fg_dispatch.h"
+
+namespace {
+thread_local char g_err[512] = "";
+
+fg_status fail(fg_status st, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return st;
+}
+
+#define FG_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail(FG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+}  // namespace
+
+struct fg_handle {
+  fg_config cfg;
+  fg::DevCfg dev;
+  int device;
+  float* d_tab_a;
+  float* d_tab_b;
+  int max_smem_optin;
+  int sm_count;
+};
+
+extern "C" {
+
+const char* fg_last_error(void) { return g_err; }
+int32_t fg_abi_version(void) { return FG_ABI_VERSION; }
+
+fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
+  if (!cfg || !out) return fail(FG_ERR_INVALID, "fg_create: null argument");
+  if (cfg->struct_size != sizeof(fg_config))
+    return fail(FG_ERR_INVALID, "fg_create: struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(fg_config));
+  if (cfg->n_dof < 1 || cfg->n_dof > FG_MAX_DOF) return fail(FG_ERR_INVALID, "n_dof %d out of range 1..%d", cfg->n_dof, FG_MAX_DOF);
+  if (cfg->n_steps < 2) return fail(FG_ERR_INVALID, "n_steps %d < 2", cfg->n_steps);
+  if (cfg->env_kind < 0 || cfg->env_kind > FG_ENV_TOY) return fail(FG_ERR_INVALID, "unknown env_kind %d", cfg->env_kind);
+  if (cfg->mp_kind < 0 || cfg->mp_kind > FG_MP_TRAJ) return fail(FG_ERR_INVALID, "unknown mp_kind %d", cfg->mp_kind);
+  if (cfg->ctrl_kind < 0 || cfg->ctrl_kind > FG_CTRL_MOTOR) return fail(FG_ERR_INVALID, "unknown ctrl_kind %d", cfg->ctrl_kind);
+  if (cfg->mp_kind != FG_MP_TRAJ && (cfg->n_basis < 1 || !cfg->tab_a || !cfg->tab_b))
+    return fail(FG_ERR_INVALID, "n_basis >= 1 and both tables are required for mp_kind %d", cfg->mp_kind);
+  if (cfg->n_obs_out < 0 || cfg->n_obs_out > FG_MAX_OBS) return fail(FG_ERR_INVALID, "n_obs_out %d out of range", cfg->n_obs_out);
+  if (cfg->env_kind == FG_ENV_HOLE_REACHER && cfg->rew_fct != 0)
+    return fail(FG_ERR_UNSUPPORTED, "hole reacher rew_fct %d not implemented (only 'simple')", cfg->rew_fct);
+
+  fg_handle* h = new (std::nothrow) fg_handle();
+  if (!h) return fail(FG_ERR_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->d_tab_a = h->d_tab_b = nullptr;
+  int prev = 0;
+  FG_CUDA(cudaGetDevice(&prev));
+  FG_CUDA(cudaSetDevice(device));
+  FG_CUDA(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  FG_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+
+  fg::DevCfg& d = h->dev;
+  memset(&d, 0, sizeof(d));
+  const int T = cfg->n_steps, K = cfg->n_basis, N = cfg->n_dof;
+  d.n_dof = N; d.T = T; d.K = K; d.max_steps = cfg->max_episode_steps;
+  d.dt = cfg->dt; d.dt_f = (float)cfg->dt;
+  const bool torque = cfg->env_kind == FG_ENV_SIMPLE_REACHER;
+  // Box(low=-bound, high=bound) with the default float32 dtype (base_reacher_direct.py:16-18, _torque.py:16-18;
+  // ToyEnv: +-1, test_black_box.py:29)
+  d.act_lim = torque ? 1000.0f : (cfg->env_kind == FG_ENV_TOY ? 1.0f : (float)(2.0 * fg::kPi));
+  for (int i = 0; i < FG_MAX_DOF; ++i) { d.p[i] = cfg->p_gains[i]; d.d[i] = cfg->d_gains[i]; }
+  d.tau = cfg->tau; d.alpha = cfg->dmp_alpha; d.beta = cfg->dmp_alpha / 4.0f;
+  d.wscale = cfg->weights_scale; d.gscale = cfg->goal_scale; d.rel_goal = cfg->relative_goal;
+  d.allow_self = cfg->allow_self_collision; d.allow_wall = cfg->allow_wall_collision;
+  d.rew_fct = cfg->rew_fct; d.wall_mode = cfg->wall_mode; d.time_aware = cfg->time_aware; d.ctrl = cfg->ctrl_kind;
+  d.penalty = cfg->collision_penalty;
+  d.n_obs_out = cfg->n_obs_out;
+  const int extra[4] = {4, 5, 3, -2};   // hole: width, ee-goal(2), steps; viapoint: 2+2+1; simple: 2+1; toy: obs dim 1
+  d.n_obs_full = 3 * N + extra[cfg->env_kind] + (cfg->time_aware ? 1 : 0);
+  if (cfg->env_kind == FG_ENV_TOY) d.n_obs_full = 1 + (cfg->time_aware ? 1 : 0);
+  for (int j = 0; j < cfg->n_obs_out; ++j) {
+    if (cfg->obs_index[j] < 0 || cfg->obs_index[j] >= d.n_obs_full) {
+      delete h;
+      return fail(FG_ERR_INVALID, "obs_index[%d]=%d outside the %d-wide step observation", j, cfg->obs_index[j], d.n_obs_full);
+    }
+    d.obs_index[j] = cfg->obs_index[j];
+  }
+  size_t na = 0, nb = 0;
+  switch (cfg->mp_kind) {
+    case FG_MP_PROMP: d.cols_a = K; d.rows_b = T - 1; d.cols_b = 1; break;
+    case FG_MP_DMP: d.cols_a = K; d.rows_b = T - 1; d.cols_b = 1; break;
+    case FG_MP_PRODMP: d.cols_a = K + 3; d.rows_b = T; d.cols_b = K + 3; break;
+    default: d.cols_a = 0; d.rows_b = 0; d.cols_b = 0; break;
+  }
+  na = (size_t)T * d.cols_a; nb = (size_t)d.rows_b * d.cols_b;
+  if (na) {
+    FG_CUDA(cudaMalloc(&h->d_tab_a, na * sizeof(float)));
+    FG_CUDA(cudaMemcpy(h->d_tab_a, cfg->tab_a, na * sizeof(float), cudaMemcpyHostToDevice));
+    FG_CUDA(cudaMalloc(&h->d_tab_b, nb * sizeof(float)));
+    FG_CUDA(cudaMemcpy(h->d_tab_b, cfg->tab_b, nb * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  d.tab_a = h->d_tab_a; d.tab_b = h->d_tab_b;
+  h->cfg.tab_a = h->cfg.tab_b = nullptr;   // host pointers are not retained
+  FG_CUDA(cudaSetDevice(prev));
+  *out = h;
+  return FG_OK;
+}
+
+fg_status fg_destroy(fg_handle* h) {
+  if (!h) return FG_OK;
+  if (h->d_tab_a) cudaFree(h->d_tab_a);
+  if (h->d_tab_b) cudaFree(h->d_tab_b);
+  delete h;
+  return FG_OK;
+}
+
+int32_t fg_num_params(const fg_handle* h) {
+  if (!h) return -1;
+  const int kp = (h->cfg.mp_kind == FG_MP_PROMP) ? h->cfg.n_basis : h->cfg.n_basis + 1;
+  return h->cfg.mp_kind == FG_MP_TRAJ ? 0 : h->cfg.n_dof * kp;
+}
+
+int32_t fg_obs_full_dim(const fg_handle* h) { return h ? h->dev.n_obs_full : -1; }
+
+fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int32_t seg_steps, void* stream) {
+  if (!h || !io) return fail(FG_ERR_INVALID, "fg_rollout: null argument");
+  if (io->struct_size != sizeof(fg_rollout_io)) return fail(FG_ERR_INVALID, "fg_rollout: io struct_size mismatch");
+  if (B < 0) return fail(FG_ERR_INVALID, "fg_rollout: negative batch");
+  if (B == 0) return FG_OK;
+  if (seg_steps < 1 || seg_steps > h->cfg.n_steps)
+    return fail(FG_ERR_INVALID, "fg_rollout: seg_steps %d outside 1..%d", seg_steps, h->cfg.n_steps);
+  const bool need_state = h->cfg.env_kind != FG_ENV_TOY;
+  if ((need_state && (!io->q || !io->v || !io->ctx)) || !io->steps || !io->done || !io->ret || !io->length ||
+      !io->flags || !io->obs || !io->info)
+    return fail(FG_ERR_INVALID, "fg_rollout: a required buffer is NULL");
+  if (h->cfg.mp_kind == FG_MP_TRAJ ? (!io->traj_pos || !io->traj_vel) : !io->params)
+    return fail(FG_ERR_INVALID, "fg_rollout: trajectory source buffer is NULL");
+  if ((io->use_cond || io->write_cond) && (!io->cond_pos || !io->cond_vel))
+    return fail(FG_ERR_INVALID, "fg_rollout: cond buffers required by use_cond/write_cond");
+  int prev = 0;
+  FG_CUDA(cudaGetDevice(&prev));
+  if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));
+  const char* why = nullptr;
+  cudaError_t e = fg::launch_rollout(h->dev, h->cfg.env_kind, h->cfg.mp_kind, *io, B, seg_steps,
+                                     (cudaStream_t)stream, h->max_smem_optin, &why);
+  if (prev != h->device) cudaSetDevice(prev);
+  if (why) return fail(FG_ERR_UNSUPPORTED, "fg_rollout: %s", why);
+  if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_rollout launch: %s", cudaGetErrorString(e));
+  return FG_OK;
+}
+
+fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_pos, const float* bc_vel,
+                     float* pos_out, float* vel_out, int64_t B, void* stream) {
+  if (!h || !params || !pos_out || !vel_out) return fail(FG_ERR_INVALID, "fg_trajgen: null argument");
+  if (h->cfg.mp_kind == FG_MP_TRAJ) return fail(FG_ERR_INVALID, "fg_trajgen: handle has no trajectory generator");
+  if (h->cfg.mp_kind != FG_MP_PROMP && (!bc_pos || !bc_vel))
+    return fail(FG_ERR_INVALID, "fg_trajgen: DMP / ProDMP need boundary conditions");
+  if (B <= 0) return B == 0 ? FG_OK : fail(FG_ERR_INVALID, "fg_trajgen: negative batch");
+  int prev = 0;
+  FG_CUDA(cudaGetDevice(&prev));
+  if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));
+  const char* why = nullptr;
+  cudaError_t e = fg::launch_trajgen(h->dev, h->cfg.mp_kind, params, bc_pos, bc_vel, pos_out, vel_out, B,
+                                     (cudaStream_t)stream, h->max_smem_optin, h->sm_count, &why);
+  if (prev != h->device) cudaSetDevice(prev);
+  if (why) return fail(FG_ERR_UNSUPPORTED, "fg_trajgen: %s", why);
+  if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_trajgen launch: %s", cudaGetErrorString(e));
+  return FG_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// FP32 FFMA probe: 8 independent register chains per thread, fully unrolled inner block.
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_ffma_probe(float* sink, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456f) sink[0] = r;   // never true: keeps the chains alive
+}
+}  // namespace
+
+extern "C" fg_status fg_ffma_probe(int32_t blocks, int32_t iters, float* sink_dev, double* flops, void* stream) {
+  if (blocks < 1 || iters < 1 || !sink_dev) return fail(FG_ERR_INVALID, "fg_ffma_probe: bad argument");
+  k_ffma_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink_dev, iters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_ffma_probe: %s", cudaGetErrorString(e));
+  if (flops) *flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+  return FG_OK;
+}

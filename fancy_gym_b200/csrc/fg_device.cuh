@@ -1,0 +1,228 @@
+// Device-side building blocks of the fused movement-primitive rollout (sm_100a).
+//
+// One CUDA thread owns one environment for a whole plan segment: MP weights, joint state and
+// the running return live in registers, the (shared) basis tables live in shared memory, and
+// nothing per-step goes to HBM.  Arithmetic follows the reference's *mixed* precision
+// (SURVEY.md App. A.6-Q7): the MP contraction and the finite-difference velocity are float32
+// (FMA chain in index order == oracle/mp.py mode 'mirror'), joint angles are integrated in
+// float64 from float32 increments exactly like base_reacher_direct.py:25-27, collision geometry
+// is float32 built from float64-reduced angles, and everything that is *reported* (distance
+// terms of the reward, end effector, observation) is recomputed in float64 on the few steps
+// where the reference reports it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fancy_gym_b200.h"
+
+namespace fg {
+
+constexpr double kPi = 3.141592653589793115997963468544185161590576171875;   // numpy.pi
+constexpr int kLinePoints = 100;                                             // hole_reacher.py:149
+
+// Kernel-side copy of fg_config (passed by value as a __grid_constant__ kernel parameter).
+struct DevCfg {
+  int n_dof, T, K, max_steps;
+  double dt;        // python float 0.01
+  float dt_f;       // float32(0.01): numpy's weak-scalar promotion when the action is float32
+  float act_lim;    // action-space bound as float32 (2*pi or 1000)
+  double p[FG_MAX_DOF], d[FG_MAX_DOF];
+  float tau, alpha, beta, wscale, gscale;
+  int rel_goal, allow_self, allow_wall, rew_fct, wall_mode, time_aware, ctrl;
+  double penalty;
+  int n_obs_out, n_obs_full;
+  int obs_index[FG_MAX_OBS];
+  const float* tab_a;   // device
+  const float* tab_b;   // device
+  int cols_a, rows_b, cols_b;
+};
+
+// ------------------------------------------------------------------------------------------
+// trigonometry: argument reduction in float64 (keeps *relative* accuracy of sin near multiples
+// of pi, where the y<0 wall predicate and the collinear-arm orientation tests live), polynomial
+// in float32.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_reduced(double th, float& s, float& c) {
+  const double kd = rint(th * 0.63661977236758138243);               // 2/pi
+  double r = fma(-kd, 1.57079632679489655800e+00, th);               // pi/2 hi
+  r = fma(-kd, 6.12323399573676603587e-17, r);                       // pi/2 lo
+  const float x = (float)r, x2 = x * x;                              // |x| <= pi/4
+  float sp = fmaf(x2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, x2, -1.6666654611e-1f);
+  sp = fmaf(sp * x2, x, x);
+  float cp = fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, x2, 4.166664568298827e-2f);
+  cp = fmaf(cp, x2, -0.5f);
+  cp = fmaf(cp, x2, 1.0f);
+  const int q = (int)kd;
+  float ss = (q & 1) ? cp : sp;
+  float cc = (q & 1) ? sp : cp;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// sin of a *relative* link angle; exactly 0 for 0, relative accuracy ~1e-7 for tiny angles
+__device__ __forceinline__ float sin_reduced(double phi) {
+  const double kd = rint(phi * 0.31830988618379069122);              // 1/pi
+  double r = fma(-kd, 3.14159265358979311600e+00, phi);
+  r = fma(-kd, 1.22464679914735317723e-16, r);
+  const float x = (float)r, x2 = x * x;                              // |x| <= pi/2
+  float p = fmaf(x2, -2.5052108e-8f, 2.7557319e-6f);
+  p = fmaf(p, x2, -1.9841270e-4f);
+  p = fmaf(p, x2, 8.3333333e-3f);
+  p = fmaf(p, x2, -1.6666667e-1f);
+  p = fmaf(p * x2, x, x);
+  return ((int)kd & 1) ? -p : p;
+}
+
+// ------------------------------------------------------------------------------------------
+// self collision (base_reacher.py:105-119, utils.py:1-9)
+// The reference tests ccw(A,B,C) = cross(B-A, C-A) > 1e-12 on joint positions.  With unit links
+// every such cross product is a sum of sines of relative link angles:
+//   ccw(J_i, J_i+1, J_m)   = sum_{l=i+1}^{m-1} sin(theta_l - theta_i)
+//   ccw(J_a, J_j,  J_j+1)  = sum_{l=a}^{j-1}   sin(theta_j - theta_l)
+// Evaluating it this way keeps float32 *relative* accuracy for (nearly) collinear links — the arm
+// starts straight (q = [q0,0,..,0]) where the position form would be pure rounding noise around
+// the 1e-12 threshold.  Exactly collinear links give exactly 0 -> "not ccw", as in the reference.
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N]) {
+  bool lim = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) lim |= (q[i] > kPi) | (q[i] < -kPi);
+  if constexpr (N < 3) {
+    return lim;
+  } else {
+    float S[N][N];   // S[i][l] = sin(th[l]-th[i]), i<l  (fully unrolled -> registers)
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int l = i + 1; l < N; ++l) S[i][l] = sin_reduced(th[l] - th[i]);
+    bool hit = false;
+    const float eps = 1e-12f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = i + 2; j < N; ++j) {
+        float c3 = 0.f;                       // ccw(A,B,C): l = i+1 .. j-1
+#pragma unroll
+        for (int l = i + 1; l <= j - 1; ++l) c3 += S[i][l];
+        const float c4 = c3 + S[i][j];        // ccw(A,B,D)
+        float c2 = 0.f;                       // ccw(B,C,D): l = i+1 .. j-1
+#pragma unroll
+        for (int l = j - 1; l >= i + 1; --l) c2 += S[l][j];
+        const float c1 = c2 + S[i][j];        // ccw(A,C,D): l = i .. j-1
+        hit |= ((c1 > eps) != (c2 > eps)) & ((c3 > eps) != (c4 > eps));
+      }
+    }
+    return lim | hit;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wall collision (hole_reacher.py:126-179): 100 samples s_m per link,
+//   x_m = fma(cos, s_m, X_i), y_m = fma(sin, s_m, Y_i);  collided iff some sample has
+//   (x<xl & y<0) | (x>xr & y<0) | (xl<x<xr & y<-depth)   (all strict).
+// s_m (float32(linspace(0,1,100))) sits in shared memory.  Both coordinates are monotone in m
+// even after rounding (fma is monotone in s), so every predicate holds on a prefix or a suffix
+// of the sample index: the exact answer follows from six binary searches instead of 100
+// evaluations (wall_mode 0); wall_mode 1 evaluates all samples literally.  Links whose lower
+// end point is not below max(0,-depth) cannot collide and are skipped in both modes.
+// ------------------------------------------------------------------------------------------
+struct Hole {
+  float xl, xr, nd;   // left edge, right edge, -depth
+};
+
+// number of samples m in [0,100) with f_m < tau (strict) or f_m <= tau, f_m = fma(k, s_m, off);
+// `rev` walks the samples backwards so that the walked sequence is non-decreasing.
+template <bool LE>
+__device__ __forceinline__ int count_below(const float* __restrict__ s_m, float k, float off, float tau, bool rev) {
+  int lo = 0, hi = kLinePoints;     // first walked index whose value is NOT below tau
+#pragma unroll
+  for (int it = 0; it < 7; ++it) {
+    const int mid = min((lo + hi) >> 1, kLinePoints - 1);
+    const int m = rev ? (kLinePoints - 1 - mid) : mid;
+    const float f = fmaf(k, s_m[m], off);
+    const bool below = LE ? (f <= tau) : (f < tau);
+    const bool active = lo < hi;
+    lo = (active && below) ? mid + 1 : lo;
+    hi = (active && !below) ? mid : hi;
+  }
+  return lo;
+}
+
+struct Span {
+  int lo, hi;   // [lo, hi) in forward sample order
+};
+__device__ __forceinline__ Span span_below(int n, bool rev) {       // {f < tau}
+  return rev ? Span{kLinePoints - n, kLinePoints} : Span{0, n};
+}
+__device__ __forceinline__ Span span_above(int n_le, bool rev) {    // {f > tau}, n_le = #{f <= tau}
+  return rev ? Span{0, kLinePoints - n_le} : Span{n_le, kLinePoints};
+}
+__device__ __forceinline__ bool overlap(Span a, Span b) { return max(a.lo, b.lo) < min(a.hi, b.hi); }
+__device__ __forceinline__ bool overlap3(Span a, Span b, Span c) {
+  return max(max(a.lo, b.lo), c.lo) < min(min(a.hi, b.hi), c.hi);
+}
+
+__device__ __forceinline__ bool link_wall_search(const float* __restrict__ s_m, float c, float s, float X, float Y,
+                                                 const Hole& h) {
+  const bool rx = c < 0.f, ry = s < 0.f;
+  const Span A = span_below(count_below<false>(s_m, c, X, h.xl, rx), rx);          // x <  xl
+  const Span Bx = span_above(count_below<true>(s_m, c, X, h.xr, rx), rx);          // x >  xr
+  const Span Gl = span_above(count_below<true>(s_m, c, X, h.xl, rx), rx);          // x >  xl
+  const Span Lr = span_below(count_below<false>(s_m, c, X, h.xr, rx), rx);         // x <  xr
+  const Span C = span_below(count_below<false>(s_m, s, Y, 0.f, ry), ry);           // y <  0
+  const Span D = span_below(count_below<false>(s_m, s, Y, h.nd, ry), ry);          // y < -depth
+  return overlap(A, C) | overlap(Bx, C) | overlap3(Gl, Lr, D);
+}
+
+__device__ __forceinline__ bool link_wall_brute(const float* __restrict__ s_m, float c, float s, float X, float Y,
+                                                const Hole& h) {
+  bool hit = false;
+#pragma unroll 4
+  for (int m = 0; m < kLinePoints; ++m) {
+    const float sm = s_m[m];
+    const float x = fmaf(c, sm, X), y = fmaf(s, sm, Y);
+    hit |= ((x < h.xl) & (y < 0.f)) | ((x > h.xr) & (y < 0.f)) | ((x > h.xl) & (x < h.xr) & (y < h.nd));
+  }
+  return hit;
+}
+
+template <int N>
+__device__ __forceinline__ bool wall_collision(const float* __restrict__ s_m, const float (&cs)[N],
+                                               const float (&sn)[N], const Hole& h, int wall_mode) {
+  bool hit = false;
+  float X = 0.f, Y = 0.f;
+  const float ythr = fmaxf(0.f, h.nd);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float X1 = fmaf(cs[i], 1.0f, X), Y1 = fmaf(sn[i], 1.0f, Y);   // sample m=99 (s=1) == next joint
+    if (fminf(Y, Y1) < ythr) {
+      hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], X, Y, h)
+                              : link_wall_brute(s_m, cs[i], sn[i], X, Y, h);
+    } else if (wall_mode == 2) {
+      hit |= link_wall_brute(s_m, cs[i], sn[i], X, Y, h);   // mode 2: no skipping at all
+    }
+    X = X1;
+    Y = Y1;
+  }
+  return hit;
+}
+
+// float64 forward kinematics of the end effector, for the steps on which the reference *reports*
+// a distance / end effector / observation (base_reacher.py:95-103, :137-139)
+template <int N>
+__device__ __forceinline__ void end_effector64(const double (&th)[N], double& ex, double& ey) {
+  ex = 0.0;
+  ey = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s, c;
+    sincos(th[i], &s, &c);
+    ex += c;
+    ey += s;
+  }
+}
+
+}  // namespace fg

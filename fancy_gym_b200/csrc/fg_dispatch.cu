@@ -1,0 +1,95 @@
+// Kernel selection for the two entry points; trajectory-generation instantiations live here.
+#include "fg_dispatch.h"
+#include "fg_trajgen.cuh"
+
+namespace fg {
+
+cudaError_t launch_rollout(const DevCfg& c, int env_kind, int mp_kind, const fg_rollout_io& io, long long B,
+                           int seg_steps, cudaStream_t stream, int max_smem_optin, const char** why) {
+  switch (env_kind) {
+    case FG_ENV_HOLE_REACHER: return launch_rollout_hole(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why);
+    case FG_ENV_VIAPOINT_REACHER: return launch_rollout_viapoint(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why);
+    case FG_ENV_SIMPLE_REACHER: return launch_rollout_simple(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why);
+    case FG_ENV_TOY: return launch_rollout_toy(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why);
+  }
+  *why = "unknown env_kind";
+  return cudaSuccess;
+}
+
+namespace {
+template <int MP, int N, int KW>
+cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel, float* pos_out,
+                          float* vel_out, long long B, cudaStream_t stream, int max_smem_optin, int sm_count,
+                          const char** why) {
+  const size_t fl = (size_t)c.T * c.cols_a + (size_t)c.rows_b * c.cols_b + (size_t)kTrajWarps * 2 * 32 * N +
+                    (KW == 0 ? (size_t)kTrajWarps * N * c.cols_a : 0);
+  const size_t smem = fl * sizeof(float);
+  if (smem > (size_t)max_smem_optin) {
+    *why = "tables exceed the shared memory of one SM";
+    return cudaSuccess;
+  }
+  auto kern = k_trajgen_closed<MP, N, KW>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  // persistent grid: a multiple of the SM count, each warp strides over envs
+  long long want = (B + kTrajWarps - 1) / kTrajWarps;
+  long long cap = (long long)sm_count * 8;
+  const unsigned blocks = (unsigned)(want < cap ? want : cap);
+  kern<<<blocks, kTrajThreads, smem, stream>>>(c, params, bc_pos, bc_vel, pos_out, vel_out, B);
+  return cudaGetLastError();
+}
+
+template <int MP, int N>
+cudaError_t launch_closed_k(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel,
+                            float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
+                            int sm_count, const char** why) {
+  constexpr int KW5 = (MP == FG_MP_PROMP) ? 5 : 8;   // the registry default num_basis = 5 (registry.py:76-125)
+  if (c.cols_a == KW5)
+    return launch_closed<MP, N, KW5>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
+  return launch_closed<MP, N, 0>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
+}
+
+template <int MP>
+cudaError_t launch_closed_n(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel,
+                            float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
+                            int sm_count, const char** why) {
+#define FG_N(n) \
+  case n: return launch_closed_k<MP, n>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
+  switch (c.n_dof) {
+    FG_N(1) FG_N(2) FG_N(3) FG_N(4) FG_N(5) FG_N(6) FG_N(7) FG_N(8)
+  }
+#undef FG_N
+  *why = "n_dof out of range";
+  return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t launch_trajgen(const DevCfg& c, int mp_kind, const float* params, const float* bc_pos, const float* bc_vel,
+                           float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
+                           int sm_count, const char** why) {
+  if (mp_kind == FG_MP_PROMP)
+    return launch_closed_n<FG_MP_PROMP>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
+  if (mp_kind == FG_MP_PRODMP)
+    return launch_closed_n<FG_MP_PRODMP>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
+  if (mp_kind == FG_MP_DMP) {
+    const size_t smem = sizeof(float) * ((size_t)c.T * c.K + (size_t)c.T);
+    if (smem > (size_t)max_smem_optin) {
+      *why = "tables exceed the shared memory of one SM";
+      return cudaSuccess;
+    }
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_trajgen_dmp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    const long long el = B * c.n_dof;
+    k_trajgen_dmp<<<(unsigned)((el + kTrajThreads - 1) / kTrajThreads), kTrajThreads, smem, stream>>>(
+        c, params, bc_pos, bc_vel, pos_out, vel_out, B);
+    return cudaGetLastError();
+  }
+  *why = "no trajectory generator for this mp_kind";
+  return cudaSuccess;
+}
+
+}  // namespace fg

@@ -1,0 +1,27 @@
+// Host-side launch dispatch: picks the kernel instantiation for (env, mp, controller dtype, dof).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fg_device.cuh"
+
+namespace fg {
+
+// Returns the CUDA error of the launch; *why is set (and nothing is launched) for a combination
+// that is not instantiated.
+cudaError_t launch_rollout(const DevCfg& c, int env_kind, int mp_kind, const fg_rollout_io& io, long long B,
+                           int seg_steps, cudaStream_t stream, int max_smem_optin, const char** why);
+
+cudaError_t launch_trajgen(const DevCfg& c, int mp_kind, const float* params, const float* bc_pos, const float* bc_vel,
+                           float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
+                           int sm_count, const char** why);
+
+// per-env translation units (compiled in parallel)
+#define FG_DECL_ENV_LAUNCH(name)                                                                              \
+  cudaError_t name(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,        \
+                   cudaStream_t stream, int max_smem_optin, const char** why)
+FG_DECL_ENV_LAUNCH(launch_rollout_hole);
+FG_DECL_ENV_LAUNCH(launch_rollout_viapoint);
+FG_DECL_ENV_LAUNCH(launch_rollout_simple);
+FG_DECL_ENV_LAUNCH(launch_rollout_toy);
+
+}  // namespace fg

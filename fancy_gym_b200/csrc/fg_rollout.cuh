@@ -1,0 +1,445 @@
+// Fused black-box rollout kernel (K1-K3 of SURVEY.md §2.1): one thread == one environment.
+//
+// Replaces, for B envs at once, the Python loop of BlackBoxWrapper.step
+// (fancy_gym/black_box/black_box_wrapper.py:150-217): trajectory evaluation (get_trajectory
+// :96-120 -> mp_pytorch), controller (:176-177), np.clip (:178-179), env.step
+// (base_reacher_direct.py:20-38 / base_reacher_torque.py:20-37), reward, termination, TimeLimit
+// truncation and reward aggregation (:215-216).
+#pragma once
+#include "fg_device.cuh"
+
+namespace fg {
+
+constexpr int kRolloutThreads = 128;
+
+// shared memory layout (floats): [tab_a T*cols_a][tab_b rows_b*cols_b][s_m 100][w  PW * blockDim]
+__host__ __device__ inline size_t rollout_smem_floats(int T, int cols_a, int rows_b, int cols_b, int pw, int threads) {
+  return (size_t)T * cols_a + (size_t)rows_b * cols_b + kLinePoints + (size_t)pw * threads;
+}
+
+// per-env weight slot count in shared memory
+template <int MP>
+__host__ __device__ inline int weight_slots(int n_dof, int K) {
+  if (MP == FG_MP_PROMP) return n_dof * K;
+  if (MP == FG_MP_DMP) return n_dof * (K + 1);
+  if (MP == FG_MP_PRODMP) return n_dof * (K + 3);   // [y_b, tau*dy_b, w_0..w_K-1, g]
+  return 0;
+}
+
+template <int ENV, int MP, bool MOTOR, int N>
+__global__ void __launch_bounds__(kRolloutThreads)
+k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
+          const int seg_steps) {
+  extern __shared__ float smem[];
+  const int T = c.T, K = c.K;
+  float* tabA = smem;
+  float* tabB = tabA + T * c.cols_a;
+  float* s_m = tabB + c.rows_b * c.cols_b;
+  float* wsm = s_m + kLinePoints;
+  const int tid = threadIdx.x, BD = blockDim.x;
+
+  // ---- stage the shared tables (coalesced) ----
+  for (int i = tid; i < T * c.cols_a; i += BD) tabA[i] = c.tab_a[i];
+  for (int i = tid; i < c.rows_b * c.cols_b; i += BD) tabB[i] = c.tab_b[i];
+  for (int i = tid; i < kLinePoints; i += BD)   // float32(numpy.linspace(0,1,100)): i*(1/99) in float64, last forced to 1
+    s_m[i] = (i == kLinePoints - 1) ? 1.0f : (float)((double)i * (1.0 / 99.0));
+
+  const long long b0 = (long long)blockIdx.x * BD;
+  const long long b = b0 + tid;
+  const bool valid = b < B;
+
+  // ---- stage this block's MP parameters: coalesced read of [BD, P], stored k-major / thread-minor ----
+  constexpr bool HAS_W = (MP != FG_MP_TRAJ);
+  const int KP = (MP == FG_MP_PROMP) ? K : K + 1;         // params per dof
+  const int P = N * KP;
+  const int WS = (MP == FG_MP_PRODMP) ? K + 3 : KP;       // smem slots per dof
+  if constexpr (HAS_W) {
+    const long long nblk = min((long long)BD, B - b0);
+    for (long long f = tid; f < nblk * P; f += BD) {
+      const int th = (int)(f / P), idx = (int)(f % P);
+      const int d = idx / KP, k = idx % KP;
+      float val = io.params[b0 * P + f];
+      if constexpr (MP == FG_MP_DMP) val = __fmul_rn(val, (k < K) ? c.wscale : c.gscale);
+      const int slot = d * WS + ((MP == FG_MP_PRODMP) ? k + 2 : k);
+      wsm[slot * BD + th] = val;
+    }
+  }
+  __syncthreads();
+  if (!valid) return;
+#define W(d, k) wsm[((d) * WS + (k)) * BD + tid]
+
+  if (io.done[b]) {   // episode already over: frozen (oracle/blackbox.py keeps such envs untouched)
+    io.ret[b] = 0.0;
+    io.length[b] = 0;
+    io.flags[b] = 0;
+    return;
+  }
+
+  // ---- per-env state ----
+  double q[N], v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if constexpr (ENV == FG_ENV_TOY) {   // ToyWrapper: current_pos = 1, current_vel = 0 (test_black_box.py:48-56)
+      q[i] = 1.0;
+      v[i] = 0.0;
+    } else {
+      q[i] = io.q[b * N + i];
+      v[i] = io.v[b * N + i];
+    }
+  }
+  int steps = io.steps[b];
+
+  // env context
+  Hole hole{};
+  double cx0 = 0, cx1 = 0, cx2 = 0, cx3 = 0;
+  if constexpr (ENV != FG_ENV_TOY) {
+    cx0 = io.ctx[b * 4 + 0]; cx1 = io.ctx[b * 4 + 1]; cx2 = io.ctx[b * 4 + 2]; cx3 = io.ctx[b * 4 + 3];
+  }
+  if constexpr (ENV == FG_ENV_HOLE_REACHER) {
+    hole.xl = (float)(cx0 - cx1 / 2);    // hole_reacher.py:152 (x - width/2), rounded once to float32
+    hole.xr = (float)(cx0 + cx1 / 2);
+    hole.nd = (float)(-cx2);
+  }
+
+  // boundary condition of the plan (black_box_wrapper.py:110-114), float32 like the library
+  float ybc[N], vbc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (io.use_cond) {
+      ybc[i] = io.cond_pos[b * N + i];
+      vbc[i] = io.cond_vel[b * N + i];
+    } else {
+      ybc[i] = (float)q[i];
+      vbc[i] = (float)v[i];
+    }
+  }
+
+  // ---- MP set-up ----
+  float dmp_y[N], dmp_yd[N];        // DMP integrator state (scaled-time velocity)
+  float pos_next[N];                // ProMP: pos[t+1] carried to the next step
+  float vel_prev[N];
+  if constexpr (MP == FG_MP_PRODMP) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      W(d, 0) = ybc[d];
+      W(d, 1) = __fmul_rn(vbc[d], c.tau);
+      if (c.rel_goal) W(d, K + 2) = __fadd_rn(W(d, K + 2), ybc[d]);
+    }
+  }
+  if constexpr (MP == FG_MP_DMP) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      dmp_y[d] = ybc[d];
+      dmp_yd[d] = __fmul_rn(vbc[d], c.tau);
+    }
+  }
+  if constexpr (MP == FG_MP_PROMP) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc = fmaf(tabA[k], W(d, k), acc);
+      pos_next[d] = acc;
+      vel_prev[d] = 0.f;
+    }
+  }
+
+  double ret = 0.0;
+  int t = 0;
+  bool terminated = false, truncated = false, success = false, collided = false;
+  float pos[N], vel[N];
+  double info0 = 0, info1 = 0;
+
+  for (; t < seg_steps; ++t) {
+    // ------------------------------------------------------------------ desired pos / vel at point t
+    if constexpr (MP == FG_MP_PROMP) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) pos[d] = pos_next[d];
+      if (t < T - 1) {
+        const float* row = tabA + (t + 1) * K;
+        const float dtt = tabB[t];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          float acc = 0.f;
+          for (int k = 0; k < K; ++k) acc = fmaf(row[k], W(d, k), acc);
+          pos_next[d] = acc;
+          vel[d] = __fdiv_rn(__fsub_rn(acc, pos[d]), dtt);
+          vel_prev[d] = vel[d];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < N; ++d) vel[d] = vel_prev[d];
+      }
+    } else if constexpr (MP == FG_MP_DMP) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        pos[d] = dmp_y[d];
+        vel[d] = __fdiv_rn(dmp_yd[d], c.tau);
+      }
+      if (t < T - 1) {   // semi-implicit Euler in scaled time (oracle/mp.py DMP._integrate)
+        const float* row = tabA + t * K;
+        const float h = tabB[t];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          float f = 0.f;
+          for (int k = 0; k < K; ++k) f = fmaf(row[k], W(d, k), f);
+          const float g = W(d, K);
+          float a = __fmul_rn(c.beta, __fsub_rn(g, dmp_y[d]));
+          a = __fmul_rn(c.alpha, __fsub_rn(a, dmp_yd[d]));
+          a = __fadd_rn(a, f);
+          dmp_yd[d] = __fadd_rn(dmp_yd[d], __fmul_rn(h, a));
+          dmp_y[d] = __fadd_rn(dmp_y[d], __fmul_rn(h, dmp_yd[d]));
+        }
+      }
+    } else if constexpr (MP == FG_MP_PRODMP) {
+      const float* rp = tabA + t * (K + 3);
+      const float* rv = tabB + t * (K + 3);
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        float ap = 0.f, av = 0.f;
+        for (int k = 0; k < K + 3; ++k) {
+          const float w = W(d, k);
+          ap = fmaf(rp[k], w, ap);
+          av = fmaf(rv[k], w, av);
+        }
+        pos[d] = ap;
+        vel[d] = __fdiv_rn(av, c.tau);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        pos[d] = io.traj_pos[(b * T + t) * N + d];
+        vel[d] = io.traj_vel[(b * T + t) * N + d];
+      }
+    }
+
+    // ------------------------------------------------------------------ controller + clip + dynamics
+    double a64[N];
+    float a32[N];
+    double acc_cost = 0.0;    // sum(acc^2) (direct envs) / sum(a^2) as the reference's dtype dictates
+    if constexpr (MOTOR) {    // pd_controller.py:28: float64 because c_pos / c_vel are float64
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double tq = __dadd_rn(__dmul_rn(c.p[i], (double)pos[i] - q[i]), __dmul_rn(c.d[i], (double)vel[i] - v[i]));
+        a64[i] = fmin(fmax(tq, -(double)c.act_lim), (double)c.act_lim);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float des = (c.ctrl == FG_CTRL_VELOCITY) ? vel[i] : pos[i];
+        a32[i] = fminf(fmaxf(des, -c.act_lim), c.act_lim);
+        a64[i] = (double)a32[i];
+      }
+    }
+
+    if constexpr (ENV == FG_ENV_HOLE_REACHER || ENV == FG_ENV_VIAPOINT_REACHER) {
+      // base_reacher_direct.py:25-27
+      if (MOTOR || steps == 0) {      // v is float64 (zeros at reset / float64 actions): float64 arithmetic
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double ac = (a64[i] - v[i]) / c.dt;
+          acc_cost += ac * ac;
+        }
+      } else {                        // float32 action and float32 velocity
+        float s32 = 0.f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float ac = __fdiv_rn(__fsub_rn(a32[i], (float)v[i]), c.dt_f);
+          s32 = __fadd_rn(s32, __fmul_rn(ac, ac));
+        }
+        acc_cost = (double)s32;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        v[i] = a64[i];
+        q[i] += MOTOR ? __dmul_rn(c.dt, a64[i]) : (double)__fmul_rn(c.dt_f, a32[i]);
+      }
+    } else if constexpr (ENV == FG_ENV_SIMPLE_REACHER) {
+      // base_reacher_torque.py:25-26
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        v[i] += MOTOR ? __dmul_rn(c.dt, a64[i]) : (double)__fmul_rn(c.dt_f, a32[i]);
+        q[i] += __dmul_rn(c.dt, v[i]);
+      }
+    }
+
+    // ------------------------------------------------------------------ geometry, collisions, reward
+    double reward = 0.0;
+    if constexpr (ENV == FG_ENV_TOY) {
+      reward = 1.0;
+    } else {
+      double th[N];
+      th[0] = q[0];
+#pragma unroll
+      for (int i = 1; i < N; ++i) th[i] = th[i - 1] + q[i];
+
+      if constexpr (ENV == FG_ENV_HOLE_REACHER) {
+        bool selfc = false, wallc = false;
+        if (!c.allow_self) selfc = self_collision<N>(q, th);
+        if (!c.allow_wall) {
+          float cs[N], sn[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) sincos_reduced(th[i], sn[i], cs[i]);
+          wallc = wall_collision<N>(s_m, cs, sn, hole, c.wall_mode);
+        }
+        collided = selfc | wallc;
+        // hr_simple_reward.py:35-53
+        double dist_cost = 0.0, coll_cost = 0.0;
+        success = false;
+        if (steps == 199 || collided) {
+          double ex, ey;
+          end_effector64<N>(th, ex, ey);
+          const double dx = ex - cx0, dy = ey - (-cx2);
+          const double dist = sqrt(dx * dx + dy * dy);
+          dist_cost = dist * dist;
+          coll_cost = collided ? 1.0 : 0.0;
+          success = (dist < 0.005) && !collided;
+        }
+        reward = __dadd_rn(__dadd_rn(__dmul_rn(dist_cost, -1.0), __dmul_rn(acc_cost, -5e-8)),
+                           __dmul_rn(coll_cost, -c.penalty));
+        terminated = collided;
+      } else if constexpr (ENV == FG_ENV_VIAPOINT_REACHER) {
+        // viapoint_reacher.py:79-107 (App. A.6-Q1/Q2: -inf start, `acc` is the action)
+        collided = c.allow_self ? false : self_collision<N>(q, th);
+        double dist = INFINITY;
+        reward = -INFINITY;
+        success = false;
+        if (!collided) {
+          if (steps == 100 || steps == 199) {
+            double ex, ey;
+            end_effector64<N>(th, ex, ey);
+            const double tx = (steps == 100) ? cx0 : cx2, ty = (steps == 100) ? cx1 : cx3;
+            dist = sqrt((ex - tx) * (ex - tx) + (ey - ty) * (ey - ty));
+          }
+          success = dist < 0.005;
+        } else {
+          double ex, ey;
+          end_effector64<N>(th, ex, ey);
+          dist = sqrt((ex - cx2) * (ex - cx2) + (ey - cx3) * (ey - cx3));
+          reward = -c.penalty;
+        }
+        reward -= dist * dist;
+        double asq;
+        if constexpr (MOTOR) {
+          asq = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) asq += a64[i] * a64[i];
+          reward -= 5e-8 * asq;
+        } else {   // float32 action: np.sum(acc**2) is float32 and 5e-8 * float32 stays float32
+          float s32 = 0.f;
+#pragma unroll
+          for (int i = 0; i < N; ++i) s32 = __fadd_rn(s32, __fmul_rn(a32[i], a32[i]));
+          reward -= (double)__fmul_rn(5e-8f, s32);
+        }
+        terminated = collided;
+      } else {   // SIMPLE_REACHER: simple_reacher.py:56-70 (collision flag is computed but unused)
+        double rdist = 0.0;
+        if (steps >= 199) {
+          double ex, ey;
+          end_effector64<N>(th, ex, ey);
+          rdist = -sqrt((ex - cx0) * (ex - cx0) + (ey - cx1) * (ey - cx1));
+        }
+        double rctrl;
+        if constexpr (MOTOR) {
+          rctrl = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) rctrl += a64[i] * a64[i];
+          reward = rdist - rctrl;
+        } else {   // float32 action: reward_ctrl float32; `0 - float32` stays float32 before steps>=199
+          float s32 = 0.f;
+#pragma unroll
+          for (int i = 0; i < N; ++i) s32 = __fadd_rn(s32, __fmul_rn(a32[i], a32[i]));
+          rctrl = (double)s32;
+          reward = (steps >= 199) ? rdist - rctrl : (double)(0.f - s32);
+        }
+        info0 = rdist;
+        info1 = rctrl;
+        terminated = false;
+      }
+    }
+    steps += 1;
+    truncated = steps >= c.max_steps;       // gymnasium TimeLimit (App. A.6-Q12)
+    ret += reward;
+
+    if (io.dbg_rewards) io.dbg_rewards[b * T + t] = reward;
+    if (io.dbg_actions) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) io.dbg_actions[(b * T + t) * N + i] = a64[i];
+    }
+    if (terminated || truncated) {
+      ++t;
+      break;
+    }
+  }
+  const int len = t;          // executed steps
+  const bool stopped = terminated || truncated;
+
+  // ---- write back state and results ----
+  if constexpr (ENV != FG_ENV_TOY) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      io.q[b * N + i] = q[i];
+      io.v[b * N + i] = v[i];
+    }
+  }
+  io.steps[b] = steps;
+  io.done[b] = stopped ? 1 : 0;
+  if (io.write_cond && len > 0 && (stopped || io.write_cond == 2)) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      io.cond_pos[b * N + i] = pos[i];
+      io.cond_vel[b * N + i] = vel[i];
+    }
+  }
+  io.ret[b] = ret;
+  io.length[b] = len;
+  io.flags[b] = (terminated ? FG_FLAG_TERMINATED : 0u) | (truncated ? FG_FLAG_TRUNCATED : 0u) |
+                (success ? FG_FLAG_SUCCESS : 0u) | (collided ? FG_FLAG_COLLIDED : 0u);
+
+  // observation after the last executed step (float64 trig, cast to float32 like _get_obs)
+  float obs[FG_MAX_OBS];
+  int no = 0;
+  if constexpr (ENV == FG_ENV_TOY) {
+    obs[no++] = -1.0f;
+  } else {
+    double th[N];
+    th[0] = q[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) th[i] = th[i - 1] + q[i];
+    double ex, ey;
+    end_effector64<N>(th, ex, ey);
+#pragma unroll
+    for (int i = 0; i < N; ++i) obs[i] = (float)cos(q[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) obs[N + i] = (float)sin(q[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) obs[2 * N + i] = (float)v[i];
+    no = 3 * N;
+    if constexpr (ENV == FG_ENV_HOLE_REACHER) {
+      obs[no++] = (float)cx1;
+      obs[no++] = (float)(ex - cx0);
+      obs[no++] = (float)(ey - (-cx2));
+      info0 = ex;
+      info1 = ey;
+    } else if constexpr (ENV == FG_ENV_VIAPOINT_REACHER) {
+      obs[no++] = (float)(ex - cx0);
+      obs[no++] = (float)(ey - cx1);
+      obs[no++] = (float)(ex - cx2);
+      obs[no++] = (float)(ey - cx3);
+      info0 = ex;
+      info1 = ey;
+    } else {
+      obs[no++] = (float)(ex - cx0);
+      obs[no++] = (float)(ey - cx1);
+    }
+    obs[no++] = (float)steps;
+  }
+  if (c.time_aware) obs[no++] = (float)((double)steps / (double)c.max_steps);
+  for (int j = 0; j < c.n_obs_out; ++j) io.obs[b * c.n_obs_out + j] = obs[c.obs_index[j]];
+  io.info[b * 4 + 0] = info0;
+  io.info[b * 4 + 1] = info1;
+  io.info[b * 4 + 2] = 0.0;
+  io.info[b * 4 + 3] = 0.0;
+#undef W
+}
+
+}  // namespace fg

@@ -1,0 +1,49 @@
+// Shared launch helper for the per-env rollout translation units.
+#pragma once
+#include "fg_dispatch.h"
+#include "fg_rollout.cuh"
+
+namespace fg {
+
+template <int ENV, int MP, bool MOTOR, int N>
+cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
+                       int max_smem_optin, const char** why) {
+  int pw = 0;
+  if (MP == FG_MP_PROMP) pw = weight_slots<FG_MP_PROMP>(N, c.K);
+  if (MP == FG_MP_DMP) pw = weight_slots<FG_MP_DMP>(N, c.K);
+  if (MP == FG_MP_PRODMP) pw = weight_slots<FG_MP_PRODMP>(N, c.K);
+  const size_t smem = sizeof(float) * rollout_smem_floats(c.T, c.cols_a, c.rows_b, c.cols_b, pw, kRolloutThreads);
+  if (smem > (size_t)max_smem_optin) {
+    *why = "tables + per-thread weights exceed the shared memory of one SM (reduce n_steps or n_basis)";
+    return cudaSuccess;
+  }
+  auto kern = k_rollout<ENV, MP, MOTOR, N>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const long long blocks = (B + kRolloutThreads - 1) / kRolloutThreads;
+  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, io, B, seg_steps);
+  return cudaGetLastError();
+}
+
+template <int ENV, int N>
+cudaError_t launch_mp_ctrl(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,
+                           cudaStream_t stream, int max_smem_optin, const char** why) {
+  const bool motor = c.ctrl == FG_CTRL_MOTOR;
+#define FG_CASE(MPK)                                                                                             \
+  case MPK:                                                                                                      \
+    return motor ? launch_one<ENV, MPK, true, N>(c, io, B, seg_steps, stream, max_smem_optin, why)               \
+                 : launch_one<ENV, MPK, false, N>(c, io, B, seg_steps, stream, max_smem_optin, why);
+  switch (mp_kind) {
+    FG_CASE(FG_MP_PROMP)
+    FG_CASE(FG_MP_DMP)
+    FG_CASE(FG_MP_PRODMP)
+    FG_CASE(FG_MP_TRAJ)
+  }
+#undef FG_CASE
+  *why = "unknown mp_kind";
+  return cudaSuccess;
+}
+
+}  // namespace fg

@@ -1,0 +1,283 @@
+"""Trajectory generators (host facade over the CUDA kernels): the role of mp_pytorch.mp.{ProMP,
+DMP, ProDMP} behind fancy_gym/black_box/factory/trajectory_generator_factory.py:7-21.
+
+The method names are the ones BlackBoxWrapper calls (black_box_wrapper.py:57,62-65,102,106,
+113-118,124,226): set_duration, set_params, set_initial_conditions, get_traj_pos, get_traj_vel,
+get_params_bounds, reset, plus the attributes phase_gn / basis_gn / tau / learn_tau.
+
+Nothing here computes a trajectory on the CPU: this class only builds the small shared tables
+(float64 -> float32, a few KB) and launches fg_trajgen; inside the fused rollout the same tables
+are evaluated per env and per step in registers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .basis_gn import NormalizedRBFBasisGenerator, ProDMPBasisGenerator
+
+
+def time_grid32(duration: float, dt: float, init_time: float) -> np.ndarray:
+    """float32 time grid exactly as the library builds it: torch.linspace(0, duration, T+1) in
+    float32, plus the float32 init_time, first point dropped."""
+    T = int(round(duration / dt))
+    grid = torch.linspace(0, float(duration), T + 1, dtype=torch.float32).numpy()
+    return (grid + np.float32(init_time)).astype(np.float32)[1:]
+
+
+class MPTables:
+    """What fg_create needs from a trajectory generator for one plan."""
+    __slots__ = ("mp_kind", "n_basis", "n_steps", "tab_a", "tab_b", "tau", "dmp_alpha", "weights_scale",
+                 "goal_scale", "relative_goal")
+
+    def __init__(self, **kw):
+        self.tau, self.dmp_alpha, self.weights_scale, self.goal_scale, self.relative_goal = 1.0, 25.0, 1.0, 1.0, 0
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class MPInterface:
+    mp_kind = -1
+
+    def __init__(self, basis_gn: NormalizedRBFBasisGenerator, num_dof: int, weights_scale: float = 1.0,
+                 device=None, **kwargs):
+        self.basis_gn = basis_gn
+        self.phase_gn = basis_gn.phase_generator
+        self.num_dof = int(num_dof)
+        self.weights_scale = weights_scale
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.duration = None
+        self.dt = None
+        self.init_time = 0.0
+        self.init_pos = None
+        self.init_vel = None
+        self.params = None
+        self._handles = {}
+
+    # ---- attributes the reference reads -----------------------------------------------------
+    @property
+    def learn_tau(self):
+        return self.phase_gn.learn_tau
+
+    @property
+    def learn_delay(self):
+        return self.phase_gn.learn_delay
+
+    @property
+    def tau(self):
+        return self.phase_gn.tau
+
+    @property
+    def _num_local_params(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def num_params(self) -> int:
+        return self.phase_gn.num_params + self._num_local_params
+
+    # ---- BlackBoxWrapper-facing API -----------------------------------------------------------
+    def reset(self):
+        self.phase_gn.reset()
+
+    def get_params_bounds(self) -> torch.Tensor:
+        lo, hi = self.phase_gn.get_params_bounds()
+        n = self._num_local_params
+        return torch.tensor([lo + [-float("inf")] * n, hi + [float("inf")] * n], dtype=torch.float32)
+
+    def set_params(self, params):
+        params = torch.as_tensor(params)
+        if params.shape[-1] != self.num_params:
+            raise ValueError(f"expected {self.num_params} params, got {tuple(params.shape)}")
+        self.params = self.phase_gn.set_params(params)
+
+    def set_initial_conditions(self, init_time, init_pos, init_vel):
+        self.init_time = float(np.asarray(init_time if not torch.is_tensor(init_time) else init_time.cpu()))
+        self.init_pos = init_pos
+        self.init_vel = init_vel
+
+    def set_duration(self, duration, dt):
+        self.dt = float(dt)
+        if duration is None:     # learn_sub_trajectories: trajectory length follows the learned tau
+            if not self.phase_gn.uniform():
+                tau = self.phase_gn.tau
+                if not bool((tau == tau.flatten()[0]).all()):
+                    raise NotImplementedError("sub-trajectory length must be the same for all envs of a batch")
+                tau0 = float(tau.flatten()[0])
+            else:
+                tau0 = self.phase_gn.scalar_tau()
+            duration = float(np.round(tau0 / dt) * dt)
+        self.duration = float(duration)
+
+    @property
+    def n_steps(self) -> int:
+        return int(round(self.duration / self.dt))
+
+    def times32(self) -> np.ndarray:
+        return time_grid32(self.duration, self.dt, self.init_time)
+
+    def tables(self) -> MPTables:
+        raise NotImplementedError
+
+    def table_key(self):
+        """identifies the shared tables of the current plan (handles are cached under it)"""
+        pg = self.phase_gn
+        if not pg.uniform():
+            raise NotImplementedError("per-env tau/delay is not supported on the table-driven kernels")
+        return (self.n_steps, round(self.init_time / self.dt), pg.scalar_tau(), pg.scalar_delay())
+
+    # ---- stand-alone trajectory generation on the GPU (fg_trajgen) ------------------------------
+    def _trajgen_handle(self):
+        key = (*self.table_key(), self.device.index or 0)
+        h = self._handles.get(key)
+        if h is None:
+            tb = self.tables()
+            cfg = _lib.FgConfig()
+            cfg.struct_size = C.sizeof(_lib.FgConfig)
+            cfg.env_kind, cfg.mp_kind, cfg.ctrl_kind = _lib.ENV_TOY, tb.mp_kind, _lib.CTRL_VELOCITY
+            cfg.n_dof, cfg.n_steps, cfg.n_basis = self.num_dof, tb.n_steps, tb.n_basis
+            cfg.max_episode_steps, cfg.dt = tb.n_steps, self.dt
+            cfg.tau, cfg.dmp_alpha = tb.tau, tb.dmp_alpha
+            cfg.weights_scale, cfg.goal_scale, cfg.relative_goal = tb.weights_scale, tb.goal_scale, tb.relative_goal
+            ta = np.ascontiguousarray(tb.tab_a, dtype=np.float32)
+            tbb = np.ascontiguousarray(tb.tab_b, dtype=np.float32)
+            cfg.tab_a, cfg.tab_b = ta.ctypes.data, tbb.ctypes.data
+            hp = C.c_void_p()
+            _lib.check(_lib.lib.fg_create(C.byref(cfg), self.device.index or 0, C.byref(hp)))
+            h = hp
+            self._handles[key] = h
+        return h
+
+    def _run_trajgen(self):
+        if self.params is None:
+            raise RuntimeError("set_params() must be called before get_traj_pos()/get_traj_vel()")
+        p = self.params.to(self.device, torch.float32)
+        batched = p.dim() == 2
+        if not batched:
+            p = p[None]
+        p = p.contiguous()
+        B, T, N = p.shape[0], self.n_steps, self.num_dof
+
+        def bc(x):
+            if x is None:
+                return None
+            x = torch.as_tensor(x).to(self.device, torch.float32)
+            return x.expand(B, N).contiguous() if x.dim() < 2 else x.contiguous()
+
+        bp, bv = bc(self.init_pos), bc(self.init_vel)
+        pos = torch.empty(B, T, N, device=self.device, dtype=torch.float32)
+        vel = torch.empty_like(pos)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib.fg_trajgen(self._trajgen_handle(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
+                                       bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(), B,
+                                       C.c_void_p(stream)))
+        return (pos, vel) if batched else (pos[0], vel[0])
+
+    def get_traj_pos(self):
+        return self._run_trajgen()[0]
+
+    def get_traj_vel(self):
+        return self._run_trajgen()[1]
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                _lib.lib.fg_destroy(h)
+        except Exception:
+            pass
+
+
+class ProMP(MPInterface):
+    """pos = (weights_scale * Phi) W^T, vel = forward finite difference over the float32 time grid,
+    last row duplicated."""
+    mp_kind = _lib.MP_PROMP
+
+    @property
+    def _num_local_params(self):
+        return self.num_dof * self.basis_gn.num_basis
+
+    def tables(self) -> MPTables:
+        t32 = self.times32()
+        b = self.basis_gn.learnable_basis32(t32)
+        tab_a = (b * np.float32(self.weights_scale)).astype(np.float32)
+        tab_b = np.diff(t32).astype(np.float32)
+        return MPTables(mp_kind=self.mp_kind, n_basis=self.basis_gn.num_basis, n_steps=len(t32), tab_a=tab_a, tab_b=tab_b,
+                        tau=self.phase_gn.scalar_tau())
+
+
+class DMP(MPInterface):
+    """Semi-implicit Euler of  y'' = alpha (beta (g - y) - y') + x Phi w  in scaled time (App. B.6)."""
+    mp_kind = _lib.MP_DMP
+
+    def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, alpha=25, **kwargs):
+        super().__init__(basis_gn, num_dof, weights_scale, **kwargs)
+        self.goal_scale = goal_scale
+        self.alpha = alpha
+        self.beta = alpha / 4
+
+    @property
+    def _num_local_params(self):
+        return self.num_dof * (self.basis_gn.num_basis + 1)
+
+    def tables(self) -> MPTables:
+        pg = self.phase_gn
+        t32 = self.times32()
+        lin = pg.linear_phase32(t32)
+        xb = (pg.phase64(lin)[:, None] * self.basis_gn.basis64(lin)).astype(np.float32)
+        sc = pg.linear_phase32(t32, clip_hi=False)            # left-bounded scaled time, float32 ops
+        tab_b = np.diff(sc).astype(np.float32)
+        return MPTables(mp_kind=self.mp_kind, n_basis=self.basis_gn.num_basis, n_steps=len(t32), tab_a=xb, tab_b=tab_b,
+                        tau=pg.scalar_tau(), dmp_alpha=float(self.alpha), weights_scale=float(self.weights_scale),
+                        goal_scale=float(self.goal_scale))
+
+
+class ProDMP(MPInterface):
+    """Closed-form DMP solution with boundary conditions (App. B.7):
+    pos = xi1 y_b + xi2 tau dy_b + H_pos [w; g],  vel = (xi3 y_b + xi4 tau dy_b + H_vel [w; g]) / tau."""
+    mp_kind = _lib.MP_PRODMP
+
+    def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, auto_scale_basis=False,
+                 relative_goal=False, disable_weights=False, disable_goal=False, **kwargs):
+        assert isinstance(basis_gn, ProDMPBasisGenerator)      # trajectory_generator_factory.py:16-17
+        if disable_weights or disable_goal:
+            raise NotImplementedError("disable_weights / disable_goal are not used by any fancy_gym config")
+        super().__init__(basis_gn, num_dof, weights_scale, **kwargs)
+        self.goal_scale = goal_scale
+        self.auto_scale_basis = auto_scale_basis
+        self.relative_goal = relative_goal
+
+    @property
+    def _num_local_params(self):
+        return self.num_dof * (self.basis_gn.num_basis + 1)
+
+    def weights_goal_scale(self) -> np.ndarray:
+        K = self.basis_gn.num_basis
+        s = np.zeros(K + 1)
+        s[:K] = self.weights_scale
+        s[K] = self.goal_scale
+        if self.auto_scale_basis:
+            s = s * self.basis_gn.auto_basis_scale_factors
+        return s
+
+    def tables(self) -> MPTables:
+        bg = self.basis_gn
+        t32 = self.times32()
+        idx = bg.indices(t32.astype(np.float64))
+        ib = bg.indices(np.float64(np.float32(self.init_time)))
+        y1, y2, dy1, dy2 = (bg.pc_y[idx, j] for j in range(4))
+        y1b, y2b, dy1b, dy2b = (bg.pc_y[ib, j] for j in range(4))
+        pb, vb = bg.pc_pos_basis[ib], bg.pc_vel_basis[ib]
+        det = y1b * dy2b - y2b * dy1b
+        xi1 = dy2b / det * y1 - dy1b / det * y2
+        xi2 = y1b / det * y2 - y2b / det * y1
+        xi3 = dy2b / det * dy1 - dy1b / det * dy2
+        xi4 = y1b / det * dy2 - y2b / det * dy1
+        s = self.weights_goal_scale()
+        pos_h = (bg.pc_pos_basis[idx] - xi1[:, None] * pb - xi2[:, None] * vb) * s
+        vel_h = (bg.pc_vel_basis[idx] - xi3[:, None] * pb - xi4[:, None] * vb) * s
+        tab_a = np.concatenate([xi1[:, None], xi2[:, None], pos_h], axis=1).astype(np.float32)
+        tab_b = np.concatenate([xi3[:, None], xi4[:, None], vel_h], axis=1).astype(np.float32)
+        return MPTables(mp_kind=self.mp_kind, n_basis=bg.num_basis, n_steps=len(t32), tab_a=tab_a, tab_b=tab_b,
+                        tau=self.phase_gn.scalar_tau(), relative_goal=int(bool(self.relative_goal)))

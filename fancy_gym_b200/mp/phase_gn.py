@@ -1,0 +1,114 @@
+"""Phase generators (host side): the role of mp_pytorch.phase_gn.{Linear,ExpDecay}PhaseGenerator
+behind fancy_gym/black_box/factory/phase_generator_factory.py:9-23.
+
+The phase itself is evaluated while the basis tables for the CUDA kernels are built
+(fancy_gym_b200/mp/basis_gn.py); this class carries tau / delay, their learnable-parameter
+bookkeeping (params are consumed from the front of the vector: tau first, delay second,
+test/test_black_box.py:168-193) and the "finalize" rule (tau/delay only change on the first
+set_params after reset(), test/test_replanning_sequencing.py:285-335).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class PhaseGenerator:
+    kind = "linear"
+
+    def __init__(self, tau: float = 3.0, delay: float = 0.0, learn_tau: bool = False, learn_delay: bool = False,
+                 tau_bound=None, delay_bound=None, **kwargs):
+        self._tau0 = float(tau)
+        self._delay0 = float(delay)
+        self.learn_tau = bool(learn_tau)
+        self.learn_delay = bool(learn_delay)
+        self.tau_bound = list(tau_bound) if tau_bound is not None else [1e-5, float("inf")]
+        self.delay_bound = list(delay_bound) if delay_bound is not None else [0.0, float("inf")]
+        self.reset()
+
+    # -- state --------------------------------------------------------------------------------
+    def reset(self):
+        """un-finalize: the next set_params() may change tau / delay again"""
+        self.tau = torch.tensor(self._tau0, dtype=torch.float32)
+        self.delay = torch.tensor(self._delay0, dtype=torch.float32)
+        self.is_finalized = False
+
+    def finalize(self):
+        self.is_finalized = True
+
+    @property
+    def num_params(self) -> int:
+        return int(self.learn_tau) + int(self.learn_delay)
+
+    def set_params(self, params: torch.Tensor) -> torch.Tensor:
+        """Consumes [tau][delay] from the front of params[..., P]; returns the remaining columns."""
+        i = 0
+        if self.learn_tau:
+            if not self.is_finalized:
+                tau = params[..., i].detach().to("cpu", torch.float32)
+                if not bool((tau > 0).all()):
+                    raise AssertionError("tau must be positive")
+                self.tau = tau
+            i += 1
+        if self.learn_delay:
+            if not self.is_finalized:
+                delay = params[..., i].detach().to("cpu", torch.float32)
+                if not bool((delay >= 0).all()):
+                    raise AssertionError("delay must be non-negative")
+                self.delay = delay
+            i += 1
+        self.finalize()
+        return params[..., i:]
+
+    def get_params_bounds(self):
+        lo, hi = [], []
+        if self.learn_tau:
+            lo.append(self.tau_bound[0]); hi.append(self.tau_bound[1])
+        if self.learn_delay:
+            lo.append(self.delay_bound[0]); hi.append(self.delay_bound[1])
+        return lo, hi
+
+    # -- numerics (float32 linear phase exactly as the library's elementwise torch ops) ---------
+    def uniform(self) -> bool:
+        """True when tau and delay are the same for every env of the batch (shared tables)."""
+        return self.tau.dim() == 0 and self.delay.dim() == 0
+
+    def scalar_tau(self) -> float:
+        return float(self.tau)
+
+    def scalar_delay(self) -> float:
+        return float(self.delay)
+
+    def linear_phase32(self, times32: np.ndarray, clip_hi: bool = True) -> np.ndarray:
+        tau, delay = np.float32(self.scalar_tau()), np.float32(self.scalar_delay())
+        z = (times32.astype(np.float32) - delay) / tau
+        return np.clip(z, 0, 1 if clip_hi else None).astype(np.float32)
+
+    def phase64(self, lin) -> np.ndarray:
+        """canonical phase in float64 from a linear phase"""
+        return np.asarray(lin, dtype=np.float64)
+
+    def unbound_phase64_of_time(self, t64):
+        """canonical phase (unbounded) of absolute times with the construction-time tau / delay"""
+        return (np.asarray(t64, dtype=np.float64) - self._delay0) / self._tau0
+
+
+class LinearPhaseGenerator(PhaseGenerator):
+    kind = "linear"
+
+
+class ExpDecayPhaseGenerator(PhaseGenerator):
+    kind = "exp"
+
+    def __init__(self, tau: float = 3.0, delay: float = 0.0, alpha_phase: float = 3.0, learn_tau: bool = False,
+                 learn_delay: bool = False, learn_alpha_phase: bool = False, **kwargs):
+        if learn_alpha_phase:
+            raise NotImplementedError("learn_alpha_phase is not used by any fancy_gym config")
+        self.alpha_phase = float(alpha_phase)
+        super().__init__(tau, delay, learn_tau, learn_delay, **kwargs)
+
+    def phase64(self, lin) -> np.ndarray:
+        return np.exp(-self.alpha_phase * np.asarray(lin, dtype=np.float64))
+
+    def unbound_phase64_of_time(self, t64):
+        return np.exp(-self.alpha_phase * super().unbound_phase64_of_time(t64))

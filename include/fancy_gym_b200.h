@@ -1,0 +1,197 @@
+/*
+ * fancy_gym_b200 — C ABI of the B200-native movement-primitive black-box rollout path.
+ *
+ * This is the drop-in boundary for ONE path of ALRhub/fancy_gym (reference v0.3.0):
+ *   BlackBoxWrapper.step(params)                fancy_gym/black_box/black_box_wrapper.py:150-217
+ *     get_trajectory -> mp_pytorch traj_gen     fancy_gym/black_box/black_box_wrapper.py:96-120
+ *     tracking controller                       fancy_gym/black_box/controller/{pd,vel,pos}_controller.py
+ *     classic_control reacher step              fancy_gym/envs/classic_control/ (all files)
+ * The reference is pure Python and has no FFI of its own; the entry points below are what a
+ * ctypes binding inside fancy_gym would call instead of the Python loops cited at each function
+ * (INTEGRATION.md shows that binding).  Plain pointers and sizes only: no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns fg_status (0 = OK, < 0 = error); fg_last_error() returns a
+ *     thread-local message.  No exceptions cross the ABI.
+ *   - the CALLER owns every device buffer (PyTorch allocates them); the library allocates only
+ *     inside fg_handle (basis / phase tables) at fg_create.  No hidden synchronisation, no
+ *     allocation per call; launches are ordered on the `stream` argument (a cudaStream_t cast
+ *     to void*, 0 = default stream).
+ *   - a handle is immutable after creation: calls are re-entrant and stream ordered.  One handle
+ *     per (config, device).
+ *   - all matrices are row-major and dense.
+ */
+#ifndef FANCY_GYM_B200_H
+#define FANCY_GYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_ABI_VERSION 1
+#define FG_MAX_DOF 8      /* links / action dimensions handled in registers */
+#define FG_MAX_OBS 40     /* 3*FG_MAX_DOF + 5 (+1 time-aware column) */
+
+typedef enum fg_status {
+  FG_OK = 0,
+  FG_ERR_INVALID = -1,      /* bad argument (maps to ValueError) */
+  FG_ERR_UNSUPPORTED = -2,  /* valid but not implemented combination (NotImplementedError) */
+  FG_ERR_CUDA = -3,         /* CUDA runtime error (RuntimeError) */
+  FG_ERR_NOMEM = -4
+} fg_status;
+
+/* step-based env restated by the fused kernel (fancy_gym/envs/classic_control/ ...) */
+typedef enum fg_env_kind {
+  FG_ENV_HOLE_REACHER = 0,     /* hole_reacher/hole_reacher.py, velocity controlled */
+  FG_ENV_VIAPOINT_REACHER = 1, /* viapoint_reacher/viapoint_reacher.py, velocity controlled */
+  FG_ENV_SIMPLE_REACHER = 2,   /* simple_reacher/simple_reacher.py, torque controlled */
+  FG_ENV_TOY = 3               /* the reference tests' ToyEnv (test/test_black_box.py:27-45): reward 1, never ends */
+} fg_env_kind;
+
+/* trajectory generator (mp_pytorch.mp.{ProMP,DMP,ProDMP}; factory:
+ * fancy_gym/black_box/factory/trajectory_generator_factory.py:7-21) */
+typedef enum fg_mp_kind {
+  FG_MP_PROMP = 0,
+  FG_MP_DMP = 1,
+  FG_MP_PRODMP = 2,
+  FG_MP_TRAJ = 3            /* desired trajectory supplied in HBM ([B,T,dof] pos and vel) */
+} fg_mp_kind;
+
+/* tracking controller (fancy_gym/black_box/factory/controller_factory.py:9-21) */
+typedef enum fg_ctrl_kind {
+  FG_CTRL_VELOCITY = 0,  /* vel_controller.py:8-9 */
+  FG_CTRL_POSITION = 1,  /* pos_controller.py:8-9 */
+  FG_CTRL_MOTOR = 2      /* pd_controller.py:21-29 */
+} fg_ctrl_kind;
+
+/* bits of the per-env `flags` output */
+#define FG_FLAG_TERMINATED 1u
+#define FG_FLAG_TRUNCATED 2u
+#define FG_FLAG_SUCCESS 4u    /* info["is_success"] of the last executed step */
+#define FG_FLAG_COLLIDED 8u   /* info["is_collided"] of the last executed step */
+
+typedef struct fg_config {
+  uint32_t struct_size;        /* sizeof(fg_config), checked */
+  int32_t env_kind;            /* fg_env_kind */
+  int32_t mp_kind;             /* fg_mp_kind */
+  int32_t ctrl_kind;           /* fg_ctrl_kind */
+  int32_t n_dof;               /* links == action dim, 1..FG_MAX_DOF */
+  int32_t n_steps;             /* T: points of one planned trajectory (times init_time + dt*(1..T)) */
+  int32_t n_basis;             /* K: weighted basis functions per dof */
+  int32_t max_episode_steps;   /* gymnasium TimeLimit of the registration (200) */
+  double dt;                   /* env.dt (base_reacher.py:21 -> 0.01) */
+
+  /* PD gains (pd_controller.py:15-19), per joint */
+  double p_gains[FG_MAX_DOF];
+  double d_gains[FG_MAX_DOF];
+
+  /* movement-primitive scalars */
+  float tau;                   /* phase tau: DMP / ProDMP velocity un-scaling */
+  float dmp_alpha;             /* DMP: alpha (25), beta = alpha/4 */
+  float weights_scale;         /* DMP: multiplies the weights in-kernel (ProMP/ProDMP fold it into the tables) */
+  float goal_scale;            /* DMP: multiplies the goal in-kernel */
+  int32_t relative_goal;       /* ProDMP: goal += init_pos */
+
+  /* env options (constructor kwargs of the reference envs) */
+  int32_t allow_self_collision;
+  int32_t allow_wall_collision;
+  double collision_penalty;
+  int32_t rew_fct;             /* hole reacher: 0 = "simple" (hr_simple_reward.py) */
+  int32_t wall_mode;           /* 0 = exact interval search over the 100 samples/link (default),
+                                  1 = literal evaluation of all 100 samples/link (hole_reacher.py:148-179) */
+  int32_t time_aware;          /* append elapsed/max_episode_steps to obs (utils/wrappers.py:49-63) */
+
+  /* observation compaction: obs_out[:, j] = full_step_obs[:, obs_index[j]] (context mask,
+   * black_box_wrapper.py:89-94) */
+  int32_t n_obs_out;
+  int32_t obs_index[FG_MAX_OBS];
+
+  /* Tables, HOST pointers, copied into the handle.  float32, row-major.
+   *   ProMP : tab_a = weights_scale * Phi            [T, K]   (learnable columns only)
+   *           tab_b = times[t+1] - times[t]          [T-1]
+   *   DMP   : tab_a = x(t) * Phi                     [T, K]
+   *           tab_b = scaled-time increments         [T-1]
+   *   ProDMP: tab_a = [xi1, xi2, H_pos(0..K)]        [T, K+3]
+   *           tab_b = [xi3, xi4, H_vel(0..K)]        [T, K+3]
+   *   TRAJ  : unused (NULL) */
+  const float* tab_a;
+  const float* tab_b;
+} fg_config;
+
+/* Buffers of one fused-rollout launch.  DEVICE pointers.  B = number of envs. */
+typedef struct fg_rollout_io {
+  uint32_t struct_size;
+  /* inputs */
+  const float* params;     /* [B, P]: per dof K weights (+ goal for DMP / ProDMP), dof-major;
+                              FG_MP_TRAJ: unused */
+  const double* ctx;       /* [B, 4]  hole: x, width, depth, -   viapoint: via_x, via_y, goal_x, goal_y
+                                      simple: goal_x, goal_y, -, -   toy: unused */
+  const float* traj_pos;   /* FG_MP_TRAJ: [B, T, dof] */
+  const float* traj_vel;   /* FG_MP_TRAJ: [B, T, dof] */
+  /* persistent per-env state, in/out (reset writes it, every plan segment continues it) */
+  double* q;               /* [B, dof] joint angles (base_reacher.py: _joint_angles) */
+  double* v;               /* [B, dof] joint velocities (_angle_velocity) */
+  int32_t* steps;          /* [B] env steps executed in this episode (_steps == TimeLimit._elapsed_steps) */
+  uint8_t* done;           /* [B] episode over (terminated or truncated earlier): env is skipped */
+  float* cond_pos;         /* [B, dof] condition_on_desired boundary values (black_box_wrapper.py:199-201) or NULL */
+  float* cond_vel;         /* [B, dof] */
+  int32_t use_cond;        /* 1: boundary condition = cond_pos/vel, 0: current q / v (black_box_wrapper.py:110-111) */
+  int32_t write_cond;      /* 1: store the desired pos/vel of the last executed step of envs that stop early */
+  /* outputs */
+  double* ret;             /* [B] sum of step rewards of this segment (black_box_wrapper.py:216, np.sum) */
+  int32_t* length;         /* [B] executed steps = infos['trajectory_length'] */
+  uint8_t* flags;          /* [B] FG_FLAG_* */
+  float* obs;              /* [B, n_obs_out] observation after the last executed step */
+  double* info;            /* [B, 4] hole/viapoint: end_effector x,y; simple: reward_dist, reward_ctrl; [2..3] spare */
+  /* optional per-step outputs of verbose>=2 (black_box_wrapper.py:208-213); NULL to skip.
+   * (infos['positions'] / ['velocities'] are the whole planned trajectory: use fg_trajgen.) */
+  double* dbg_actions;     /* [B, T, dof] infos['step_actions'] */
+  float* dbg_obs;          /* [B, T, n_obs_full] infos['step_observations'] */
+  double* dbg_rewards;     /* [B, T] infos['step_rewards'] */
+} fg_rollout_io;
+
+typedef struct fg_handle fg_handle;
+
+const char* fg_last_error(void);
+int32_t fg_abi_version(void);
+
+/* Builds the immutable per-config handle on `device` (tables are uploaded synchronously here). */
+fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out);
+fg_status fg_destroy(fg_handle* h);
+
+/* Number of params per env the handle expects (P) and width of the full step observation. */
+int32_t fg_num_params(const fg_handle* h);
+int32_t fg_obs_full_dim(const fg_handle* h);
+
+/*
+ * Fused episode (segment) rollout — replaces the T-iteration Python loop of
+ * BlackBoxWrapper.step (black_box_wrapper.py:150-217) together with get_trajectory (:96-120),
+ * controller.get_action, np.clip (:176-179) and env.step
+ * (base_reacher_direct.py:20-38 / base_reacher_torque.py:20-37) for B envs.
+ * Executes at most `seg_steps` (<= n_steps) steps per env; an env stops earlier when it
+ * terminates or hits max_episode_steps.  One CUDA thread owns one env; nothing per-step is
+ * written to HBM unless a dbg_* pointer is given.
+ */
+fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int32_t seg_steps, void* stream);
+
+/*
+ * Stand-alone trajectory generation — replaces traj_gen.get_traj_pos()/get_traj_vel()
+ * (black_box_wrapper.py:117-118).  bc_pos/bc_vel [B,dof] are the initial conditions passed to
+ * set_initial_conditions (:113-114; ignored by ProMP, may be NULL).  pos_out/vel_out [B,T,dof].
+ */
+fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_pos, const float* bc_vel,
+                     float* pos_out, float* vel_out, int64_t B, void* stream);
+
+/*
+ * FP32 FFMA-chain microbenchmark used as the roofline denominator of the fused rollout
+ * (MEASURED_PEAKS.json has no CUDA-core figure).  Runs `iters` dependent FMA rounds of 8
+ * independent chains per thread on `blocks` x 256 threads; *flops = 2 * fmas executed.
+ */
+fg_status fg_ffma_probe(int32_t blocks, int32_t iters, float* sink_dev, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FANCY_GYM_B200_H */

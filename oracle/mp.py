@@ -289,7 +289,7 @@ class ProDMPBasis(NormalizedRBFBasis):
         pc_times = z * tau + delay
         lin = np.clip((pc_times - delay) / tau, 0, 1)
         x = np.exp(-float(pg.alpha0) * lin)
-        cen, bw = self.centres_p.astype(F64), self.bandwidth.astype(F64)
+        cen, bw = _gold_centres(self)
         b = np.exp(-((x[:, None] - cen) ** 2 * bw) / 2)
         if self._num_basis > 1:
             b = b / b.sum(axis=1, keepdims=True)

@@ -1,0 +1,208 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C-ABI
+library via the fancy_gym_b200 facade, against the CPU oracle and the committed golden vectors.
+
+Tolerances (north_star): trajectories / joint states within 1e-5 relative, where "relative" is
+|diff| <= 1e-5 * max(|ref|, scale) with scale = 1 for trajectories and pi for angles (angles cross
+zero); collision / termination flags and step counts bit-exact except where the
+oracle's decision margin is below 1e-5 (documented boundary ties), whose count is bounded.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle.blackbox import make_oracle  # noqa: E402
+from tests.golden.make_golden import BB_CASES  # noqa: E402
+
+TIE_EPS = 1e-5
+
+
+def _fg():
+    import fancy_gym_b200 as fancy_gym
+    return fancy_gym
+
+
+def rel_err(a, b, scale=1.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), scale)
+
+
+P_OF = {"fancy_ProMP/HoleReacher-v0": 25, "fancy_DMP/ViaPointReacher-v0": 30, "fancy_ProDMP/SimpleReacher-v0": 12}
+
+
+# --------------------------------------------------------------------------------------------
+# stand-alone trajectory generation (fg_trajgen, K4)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_id", list(P_OF))
+def test_trajgen_matches_oracle(env_id):
+    fancy_gym = _fg()
+    B = 257                      # ragged: not a multiple of the warp / block size
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0")
+    env.reset(seed=0)
+    rng = np.random.default_rng(3)
+    params = (0.7 * rng.standard_normal((B, P_OF[env_id]))).astype(np.float32)
+    pos, vel = env.get_trajectory(torch.as_tensor(params, device="cuda:0"))
+    pos, vel = pos.cpu().numpy(), vel.cpu().numpy()
+    out = {}
+    for mode in ("mirror", "shipped", "gold"):
+        orc = make_oracle(env_id, mode=mode)
+        orc.reset(seeds=range(B))
+        out[mode] = orc.get_trajectory(params)
+    # mirror mode is the kernel's specification: bit-exact
+    assert np.array_equal(pos, out["mirror"][0]), np.abs(pos - out["mirror"][0]).max()
+    assert np.array_equal(vel, out["mirror"][1]), np.abs(vel - out["mirror"][1]).max()
+    # the library's float32 path and the float64 definition
+    for mode in ("shipped", "gold"):
+        assert rel_err(pos, out[mode][0]).max() < 1e-5
+        # velocities are float32 finite differences (ProMP) / recurrences (DMP) in the reference itself;
+        # their own rounding noise is ~|pos| * 2^-24 / dt ~ 1e-5 absolute
+        vscale = max(1.0, np.abs(out["gold"][1]).max())
+        assert rel_err(vel, out[mode][1], scale=vscale).max() < 3e-5
+
+
+def test_trajgen_empty_and_single():
+    fancy_gym = _fg()
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=1, device="cuda:0")
+    env.reset(seed=5)
+    params = np.zeros(25, dtype=np.float32)
+    pos, vel = env.get_trajectory(params)
+    assert pos.shape == (1, 200, 5) and float(pos.abs().max()) == 0.0 and float(vel.abs().max()) == 0.0
+
+
+# --------------------------------------------------------------------------------------------
+# fused rollout against the golden vectors produced from the reference's own files
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", BB_CASES, ids=[c[0] for c in BB_CASES])
+def test_rollout_matches_reference_goldens(case, golden_dir):
+    fancy_gym = _fg()
+    fname, env_id, seeds, bbk = case
+    g = np.load(os.path.join(golden_dir, fname + ".npz"))
+    override = {"black_box_kwargs": dict(bbk)} if bbk else {}
+    B = len(seeds)
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override=override)
+    obs0, _ = env.reset(seed=np.array(seeds), options={"as_numpy": True})
+    assert np.allclose(obs0, g["obs0"], rtol=0, atol=1e-6)
+    n_plans = g["params"].shape[1]
+    for i in range(n_plans):
+        live = i < g["n_calls"]
+        if not live.any():
+            break
+        obs, ret, te, tr, info = env.step(g["params"][:, i])
+        for b in np.nonzero(live)[0]:
+            assert info["trajectory_length"][b] == g["length"][b, i], (fname, b, i)
+            assert bool(te[b]) == bool(g["terminated"][b, i]) and bool(tr[b]) == bool(g["truncated"][b, i])
+            r_ref = g["ret"][b, i]
+            if np.isfinite(r_ref):
+                assert rel_err(ret[b], r_ref).max() < 1e-5, (fname, b, i, ret[b], r_ref)
+            else:
+                assert ret[b] == r_ref
+            oscale = np.maximum(1.0, np.abs(g["obs"][b, i]))
+            assert (np.abs(obs[b] - g["obs"][b, i]) <= 2e-5 * oscale).all(), (fname, b, i, obs[b], g["obs"][b, i])
+
+
+# --------------------------------------------------------------------------------------------
+# fused rollout against the oracle on seeded random inputs (thousands of envs)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_id,sigma", [("fancy_ProMP/HoleReacher-v0", 0.25), ("fancy_ProMP/HoleReacher-v0", 1.0),
+                                          ("fancy_DMP/ViaPointReacher-v0", 1.0), ("fancy_ProDMP/SimpleReacher-v0", 1.0)])
+def test_rollout_matches_oracle_random(env_id, sigma):
+    fancy_gym = _fg()
+    B = 2048 + 37
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0")
+    env.reset(seed=100)
+    rng = np.random.default_rng(11)
+    params = (sigma * rng.standard_normal((B, P_OF[env_id]))).astype(np.float32)
+    obs, ret, te, tr, info = env.step(torch.as_tensor(params, device="cuda:0"))
+    obs, ret, te, tr = obs.cpu().numpy(), ret.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
+    length = info["trajectory_length"].cpu().numpy()
+
+    orc = make_oracle(env_id, mode="mirror")
+    orc.reset(seeds=100 + np.arange(B))
+    o_obs, o_ret, o_te, o_tr, o_info = orc.step(params)
+    tie = o_info["min_margin"] < TIE_EPS
+    agree = (length == o_info["trajectory_length"]) & (te == o_te) & (tr == o_tr)
+    assert (agree | tie).all(), f"{(~(agree | tie)).sum()} flag/length mismatches outside boundary ties"
+    assert (~agree).sum() <= max(2, B // 500), f"too many boundary ties resolved differently: {(~agree).sum()}"
+    m = agree
+    fin = m & np.isfinite(o_ret)
+    assert rel_err(ret[fin], o_ret[fin]).max() < 1e-5
+    assert np.array_equal(ret[m & ~np.isfinite(o_ret)], o_ret[m & ~np.isfinite(o_ret)])
+    oscale = np.maximum(1.0, np.abs(o_obs[m]))
+    assert (np.abs(obs[m] - o_obs[m]) <= 1e-5 * oscale).all()
+    for k in ("is_success", "is_collided"):
+        if k in info:
+            assert np.array_equal(info[k].cpu().numpy()[m], o_info[k][m])
+    if "end_effector" in info:
+        assert rel_err(info["end_effector"].cpu().numpy()[m], o_info["end_effector"][m], scale=5.0).max() < 1e-5
+    if "reward_dist" in info:
+        assert rel_err(info["reward_dist"].cpu().numpy()[m], o_info["reward_dist"][m]).max() < 1e-5
+        assert rel_err(info["reward_ctrl"].cpu().numpy()[m], o_info["reward_ctrl"][m]).max() < 1e-5
+
+
+# --------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes
+# --------------------------------------------------------------------------------------------
+def _run(env, params, seed):
+    env.reset(seed=seed)
+    obs, ret, te, tr, info = env.step(params)
+    return obs.clone(), ret.clone(), te.clone(), tr.clone(), info["trajectory_length"].clone()
+
+
+def test_wall_modes_agree_at_full_size():
+    """The interval-search wall test (mode 0) must give exactly the flags of the literal 100-samples-per-link
+    evaluation (mode 1: with the exact skip of links above ground, mode 2: no skipping at all)."""
+    fancy_gym = _fg()
+    B = 65536
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    params = torch.randn(B, 25, generator=gen, device="cuda:0")
+    outs = []
+    for mode in (0, 1, 2):
+        env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device="cuda:0", context_sampler="device",
+                             mp_config_override={"black_box_kwargs": {"wall_mode": mode}})
+        outs.append(_run(env, params, 7))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+    assert int(outs[0][2].sum()) > B // 10      # the comparison saw many collisions
+
+
+def test_determinism_and_shard_equivalence():
+    """Same inputs -> identical outputs; a batch split in two halves == the full batch (envs are independent)."""
+    fancy_gym = _fg()
+    B = 65536
+    gen = torch.Generator(device="cuda:0").manual_seed(1)
+    params = 0.5 * torch.randn(B, 25, generator=gen, device="cuda:0")
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device="cuda:0", context_sampler="device")
+    a = _run(env, params, 3)
+    b = _run(env, params, 3)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    ctx, q0 = env.unwrapped.ctx.clone(), None
+    env.reset(seed=3)
+    q0 = env.unwrapped.q[:, 0].clone()
+    half = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B // 2, device="cuda:0")
+    for lo in (0, B // 2):
+        sl = slice(lo, lo + B // 2)
+        half.reset(options={"contexts": dict(x=ctx[sl, 0].cpu().numpy(), width=ctx[sl, 1].cpu().numpy(),
+                                             depth=ctx[sl, 2].cpu().numpy(), q0=q0[sl].cpu().numpy())})
+        obs, ret, te, tr, info = half.step(params[sl])
+        assert torch.equal(ret, a[1][sl]) and torch.equal(info["trajectory_length"], a[4][sl])
+        assert torch.equal(te, a[2][sl]) and torch.equal(obs, a[0][sl])
+
+
+def test_zero_params_keep_the_arm_still():
+    """All-zero ProMP weights: zero velocity, the straight arm never collides with itself (collinear links,
+    exact zeros in the orientation tests), 200 steps, return == -dist^2 of the start pose."""
+    fancy_gym = _fg()
+    B = 1024
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device="cuda:0")
+    env.reset(seed=0)
+    ee0 = env.unwrapped.end_effector()
+    goal = torch.stack([env.unwrapped.ctx[:, 0], -env.unwrapped.ctx[:, 2]], dim=1)
+    obs, ret, te, tr, info = env.step(torch.zeros(B, 25, device="cuda:0"))
+    assert bool((info["trajectory_length"] == 200).all()) and not bool(te.any()) and bool(tr.all())
+    want = -((ee0 - goal) ** 2).sum(1)
+    assert torch.allclose(ret, want, rtol=1e-12, atol=0)
