@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the movement-primitive black-box rollout path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch: B = 65,536 episodes per GPU of
+fancy_ProMP/HoleReacher-v0 (BASELINE.json configs[1]) = trajectory generation + velocity controller
++ reacher dynamics + collision tests + reward aggregation for up to 200 env steps per episode, on
+synthetic random MP parameters (sigma * N(0,1), torch Philox) and random task contexts.
+
+Prints ONE JSON line (see README / DESIGN.md "Measurement" for the keys):
+  value            whole-job env-steps/s with inputs resident in HBM (device-timed, max over ranks)
+  e2e              the same metric through the public API (fancy_gym_b200.make(...).reset()/step()) from pinned
+                   HOST buffers, H2D of the parameters and D2H of returns / lengths / flags inside the timed region
+  roofline         fused rollout kernel: algorithmic ops (4356 per HoleReacher/ProMP env step)
+                   / measured kernel time, against the FP32 FFMA peak measured in the same run (fg_ffma_probe)
+  roofline_trajgen trajectory-only kernel (fg_trajgen): algorithmic bytes (8 B per (t, dof)) / time vs measured HBM GB/s
+  cpu_baseline     the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1, bounded sample)
+Multi-GPU (torchrun, one rank per GPU): the env batch is sharded, no data-path collective; per-step returns /
+lengths / flags are all-gathered over NCCL inside the timed region ("scaling": "weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_ID = "fancy_ProMP/HoleReacher-v0"
+B_PER_GPU = 65536
+N_PARAMS = 25
+SIGMA = 0.25
+CPU_BATCH = 64                   # envs per oracle call in the CPU baseline (numpy-vectorised port)
+OPS_PER_ENV_STEP = 4356          # SURVEY.md §8d, HoleReacher/ProMP (FMA = 2, each collision test once per step)
+TRAJ_BYTES_PER_ENV = 2 * 200 * 5 * 4 + N_PARAMS * 4   # fg_trajgen: pos + vel out, params in
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path, one worker process per host core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed0, n_batches, batch, sigma = args
+    import numpy as np
+    from oracle.blackbox import make_oracle
+    orc = make_oracle(ENV_ID, mode="shipped")
+    orc.env.compute_margins = False          # time the reference's work only: no oracle-side margin bookkeeping,
+    orc.env.double_collision_eval = True     # and both collision tests twice per step as the reference does (Q3)
+    steps = 0
+    t0 = time.perf_counter()
+    for e in range(n_batches):
+        s = seed0 + e * batch
+        orc.reset(seeds=range(s, s + batch))
+        th = (sigma * np.random.default_rng(1234 + s).standard_normal((batch, N_PARAMS))).astype(np.float32)
+        _, _, _, _, info = orc.step(th)
+        steps += int(info["trajectory_length"].sum())
+    return steps, n_batches * batch, time.perf_counter() - t0
+
+
+def cpu_reference_sample(n_batches, batch=CPU_BATCH, sigma=SIGMA):
+    """The oracle port of the reference path on ALL host cores: one worker process per core, each stepping `batch`
+    envs at a time through oracle/blackbox.py (BlackBoxWrapper.step loop, black_box_wrapper.py:150-217).
+    batch=1 has the reference's structure (one env per process, ~1.2k env-steps/s/core here; the reference's own files
+    reach ~2.1k/core); the default batch of 64 lets numpy vectorise over envs and is several times
+    FASTER per env than the reference itself, i.e. a deliberately strong CPU baseline."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(10_000_000 + 1000 * w, 1, min(batch, 4), sigma) for w in range(cores)])   # warm-up
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(100_000 * w, n_batches, batch, sigma) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    eps = sum(r[1] for r in res)
+    return dict(value=steps / wall, unit="env-steps/s", cores=cores, kind="port",
+                episodes_per_s=eps / wall, wall_s=wall, env_steps=steps, episodes=eps,
+                sample=f"{eps} episodes ({steps} env steps) of {ENV_ID}, sigma={sigma}: {cores} worker processes x {n_batches} "
+                       f"batches of {batch} envs through oracle/blackbox.py ('shipped' float32 MP, collision tests twice per step "
+                       f"like the reference)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._loop, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU path (oracle port: the reference is Python and /root/reference does not
+    travel to the GPU box) on all host cores; each step is a bounded sample of the workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 2)):
+        cpu_reference_sample(1)
+    tot_steps = tot_eps = busy = 0.0
+    for _ in range(args.steps):
+        r = cpu_reference_sample(1)
+        tot_steps += r["env_steps"]; tot_eps += r["episodes"]; busy += r["wall_s"]
+    value = tot_steps / max(busy, 1e-9)
+    scalar = cpu_reference_sample(2, batch=1)
+    line = dict(metric="env-steps/sec (fancy_ProMP/HoleReacher-v0 MP black-box rollout)", value=value, unit="env-steps/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * busy / max(args.steps, 1),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=f"{ENV_ID}, bounded CPU sample per step: {CPU_BATCH} envs x {cores} worker processes, sigma={SIGMA}"),
+                episodes_per_s=tot_eps / max(busy, 1e-9),
+                cpu_baseline=dict(value=value, unit="env-steps/s", cores=cores, kind="port",
+                                  sample=f"{args.steps} steps x {CPU_BATCH * cores} episodes; numpy-vectorised oracle port, {CPU_BATCH} envs per "
+                                         f"worker call (stronger than the reference's one-env-per-process loop)",
+                                  scalar_port_value=scalar["value"]),
+                e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=B_PER_GPU)
+    ap.add_argument("--sigma", type=float, default=SIGMA)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fancy_gym_b200 as fancy_gym
+    from fancy_gym_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+
+    env = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device")
+    base = env.unwrapped
+    # rotating input sets so that every timed step reads inputs that are cold in the 126 MB L2
+    set_bytes = B * (N_PARAMS * 4 + 5 * 8 * 2 + 4 * 8 + 5)
+    n_sets = max(2, int(np.ceil(2 * 126e6 / set_bytes)))
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sets = []
+    for s in range(n_sets):
+        env.reset(seed=10_000 * (rank + 1) + s)
+        sets.append(dict(params=(args.sigma * torch.randn(B, N_PARAMS, generator=gen, device=dev)).contiguous(),
+                         q=base.q.clone(), ctx=base.ctx.clone()))
+
+    def load_state(s):
+        base.q.copy_(s["q"]); base.ctx.copy_(s["ctx"]); base.v.zero_(); base.steps.zero_(); base.done.zero_()
+
+    gathered = None
+    if world > 1:
+        pack = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+        gathered = torch.zeros(world * B, 3, dtype=torch.float32, device=dev)
+
+    def step_device(s):
+        load_state(s)
+        env.launch(s["params"])
+        if world > 1:       # returns / lengths / flags of every rank to every rank (NCCL all-gather over NVLink)
+            pack[:, 0] = env._ret.to(torch.float32); pack[:, 1] = env._len.to(torch.float32); pack[:, 2] = env._flags.to(torch.float32)
+            dist.all_gather_into_tensor(gathered, pack)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-timed value ----------------
+    for i in range(W):
+        step_device(sets[i % n_sets])
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    total_steps = torch.zeros((), dtype=torch.int64, device=dev)
+    clk = ClockSampler(local_rank)
+    clk.__enter__()            # sampled until the end of the e2e loop (every timed region of this run)
+    if True:
+        sync_all()
+        t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for i in range(K):
+            s = sets[(W + i) % n_sets]
+            load_state(s)
+            kev[i][0].record()
+            env.launch(s["params"])
+            kev[i][1].record()
+            if world > 1:
+                pack[:, 0] = env._ret.to(torch.float32); pack[:, 1] = env._len.to(torch.float32); pack[:, 2] = env._flags.to(torch.float32)
+                dist.all_gather_into_tensor(gathered, pack)
+            total_steps += env._len.sum()
+        t_end.record()
+        sync_all()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
+    env_steps = int(total_steps.item())
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    n = torch.tensor([float(env_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    elapsed_ms_max, env_steps_all = float(t.item()), float(n.item())
+    value = env_steps_all / (elapsed_ms_max * 1e-3)
+    episodes_per_s = world * B * K / (elapsed_ms_max * 1e-3)
+
+    # ---------------- FP32 peak probe + roofline of the rollout kernel ----------------
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    flops = C.c_double()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    best = 0.0
+    for rep in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(_lib.lib.fg_ffma_probe(sm_count * 8, 4000, sink.data_ptr(), C.byref(flops), stream))
+        b.record()
+        torch.cuda.synchronize(dev)
+        if rep:
+            best = max(best, flops.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+    fp32_peak = best
+    steps_per_launch = env_steps / K
+    achieved = OPS_PER_ENV_STEP * steps_per_launch / (kernel_ms * 1e-3) / 1e12
+    roofline = dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak if fp32_peak else None,
+                    traffic=None, kernel="k_rollout<HOLE_REACHER, PROMP, vel, 5>", kernel_ms=kernel_ms,
+                    peak_source="FFMA chain probe measured in this run (fg_ffma_probe); MEASURED_PEAKS.json has no CUDA-core figure",
+                    note="achieved counts ALGORITHMIC ops: 4356 per env step incl. the literal 500 wall samples; the kernel uses an "
+                         "exact-equivalent interval search, so frac is not a pipe utilisation (see profiles/ for ncu pipe numbers)")
+
+    # ---------------- trajectory-only kernel vs HBM ----------------
+    hbm_peak, hbm_src = measured_peaks()
+    Bt = 1 << 18
+    tp = (args.sigma * torch.randn(Bt, N_PARAMS, generator=gen, device=dev)).contiguous()
+    env.traj_gen.set_params(tp); env.traj_gen.set_initial_conditions(0.0, None, None); env.traj_gen.set_duration(2.0, 0.01)
+    for _ in range(3):
+        env.traj_gen.get_traj_pos()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    a.record()
+    for _ in range(reps):
+        pos_vel = env.traj_gen._run_trajgen()
+    b.record()
+    torch.cuda.synchronize(dev)
+    del pos_vel
+    traj_ms = a.elapsed_time(b) / reps
+    traj_gbs = Bt * TRAJ_BYTES_PER_ENV / (traj_ms * 1e-3) / 1e9
+    roofline_traj = dict(bound="hbm", achieved=traj_gbs, peak=hbm_peak, unit="GB/s", frac=traj_gbs / hbm_peak, traffic=None,
+                         kernel="k_trajgen_closed<PROMP,5,5>", kernel_ms=traj_ms, peak_source=hbm_src,
+                         trajectories_per_s=Bt / (traj_ms * 1e-3), workload=f"{Bt} ProMP trajectories [200,5] pos+vel (2.1 GB output, > L2)")
+
+    # ---------------- end to end through the public API from host buffers ----------------
+    host_params = [torch.empty(B, N_PARAMS, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for hp, s in zip(host_params, sets):
+        hp.copy_(s["params"].cpu())
+    host_ret = torch.empty(B, dtype=torch.float64).pin_memory()
+    host_len = torch.empty(B, dtype=torch.int32).pin_memory()
+    host_flags = torch.empty(B, dtype=torch.bool).pin_memory()
+
+    def step_e2e(i):
+        env.reset(seed=None)                                          # fresh contexts (device Philox sampler)
+        p = host_params[i % 2].to(dev, non_blocking=True)             # H2D
+        obs, ret, te, tr, info = env.step(p)                          # public API
+        host_ret.copy_(ret, non_blocking=True)                        # D2H
+        host_len.copy_(info["trajectory_length"], non_blocking=True)
+        host_flags.copy_(te, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()                  # the caller reads the returns
+        return int(host_len.sum())
+
+    for i in range(W):
+        step_e2e(i)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for i in range(K):
+        e2e_steps += step_e2e(i)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    clk.__exit__()
+    te2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    ne2e = torch.tensor([float(e2e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ne2e, op=dist.ReduceOp.SUM)
+    e2e = dict(value=float(ne2e.item()) / float(te2e.item()), unit="env-steps/s", h2d_bytes_per_step=B * N_PARAMS * 4,
+               d2h_bytes_per_step=B * (8 + 4 + 1), episodes_per_s=world * B * K / float(te2e.item()),
+               ms_per_step=1e3 * float(te2e.item()) / K,
+               api="fancy_gym_b200.make(...).reset() + .step(params from pinned host memory) + D2H of return/length/terminated")
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(2, sigma=args.sigma)
+        cpu["scalar_port_value"] = cpu_reference_sample(2, batch=1, sigma=args.sigma)["value"]
+
+    if rank == 0:
+        line = dict(metric="env-steps/sec (fancy_ProMP/HoleReacher-v0 MP black-box rollout)", value=value, unit="env-steps/s",
+                    n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms_max / K, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=f"{ENV_ID}, {B} envs per GPU (BASELINE configs[1]), one fused rollout launch per step",
+                                envs_per_gpu=B, n_params=N_PARAMS, sigma=args.sigma, max_episode_steps=200,
+                                contexts="device Philox sampler", parallelism=f"env-shard x{world}",
+                                l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
+                                collective="all_gather(return,length,flags) per step" if world > 1 else "none"),
+                    episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B),
+                    roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e,
+                    clocks=clk.summary(), gpu_launches=K)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -223,6 +223,33 @@ class BlackBoxWrapper(Wrapper):
         tg.set_initial_conditions(init_time, self._base.q, self._base.v)   # current_pos / current_vel (:110-111)
         tg.set_duration(duration, self.dt)
 
+    def launch(self, params, seg_steps=None, replan_break=False, dbg=None):
+        """Enqueues ONE fused rollout (fg_rollout) for the current plan on the current CUDA stream and returns
+        immediately; results land in the wrapper's device buffers (_ret, _len, _flags, _obs, _info).
+        `params` [B, P_local] float32 on the device (phase parameters already stripped)."""
+        base = self._base
+        B = self.num_envs
+        T = self.traj_gen.n_steps
+        h = self._handle()
+        if self._obs is None or self._obs.shape[1] != len(self._obs_index()):
+            self._obs = torch.zeros(B, len(self._obs_index()), dtype=torch.float32, device=self.device)
+        io = _lib.FgRolloutIO()
+        io.struct_size = C.sizeof(_lib.FgRolloutIO)
+        io.params = params.data_ptr()
+        io.ctx = base.ctx.data_ptr()
+        io.q, io.v, io.steps, io.done = base.q.data_ptr(), base.v.data_ptr(), base.steps.data_ptr(), base.done.data_ptr()
+        io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
+        io.use_cond = int(self.condition_set)
+        io.write_cond = (2 if replan_break else 1) if self.condition_on_desired else 0
+        io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
+        io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
+        if dbg is not None:
+            io.dbg_rewards = dbg["rewards"].data_ptr()
+            if "actions" in dbg:
+                io.dbg_actions = dbg["actions"].data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(T if seg_steps is None else seg_steps), C.c_void_p(stream)))
+
     def step(self, action):
         base = self._base
         params, as_numpy, scalar = self._prepare_params(action)
@@ -231,31 +258,14 @@ class BlackBoxWrapper(Wrapper):
         T = self.traj_gen.n_steps
         self.plan_steps += 1
         seg, replan_break = self._segment_steps(T)
-        h = self._handle()
-
         B, n = self.num_envs, base.n_links
-        if self._obs is None or self._obs.shape[1] != len(self._obs_index()):
-            self._obs = torch.zeros(B, len(self._obs_index()), dtype=torch.float32, device=self.device)
-        io = _lib.FgRolloutIO()
-        io.struct_size = C.sizeof(_lib.FgRolloutIO)
-        io.params = local.data_ptr()
-        io.ctx = base.ctx.data_ptr()
-        io.q, io.v, io.steps, io.done = base.q.data_ptr(), base.v.data_ptr(), base.steps.data_ptr(), base.done.data_ptr()
-        io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
-        io.use_cond = int(self.condition_set)
-        io.write_cond = (2 if replan_break else 1) if self.condition_on_desired else 0
-        io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
-        io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
         dbg = None
         need_rewards = self.verbose >= 2 or self.reward_aggregation not in (np.sum, np.mean, sum)
         if need_rewards:
             dbg = dict(rewards=torch.zeros(B, T, dtype=torch.float64, device=self.device))
-            io.dbg_rewards = dbg["rewards"].data_ptr()
             if self.verbose >= 2:
                 dbg["actions"] = torch.zeros(B, T, n, dtype=torch.float64, device=self.device)
-                io.dbg_actions = dbg["actions"].data_ptr()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(seg), C.c_void_p(stream)))
+        self.launch(local, seg, replan_break, dbg)
         if self.condition_on_desired:
             self.condition_set = True      # every live env breaks at the same step or is done
 

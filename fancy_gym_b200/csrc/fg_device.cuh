@@ -75,6 +75,16 @@ __device__ __forceinline__ float sin_reduced(double phi) {
   return ((int)kd & 1) ? -p : p;
 }
 
+// x / d with a pre-computed r = RN(1/d) (__frcp_rn): one Newton step on the quotient gives the correctly
+// rounded IEEE quotient for finite, non-denormal operands (Markstein) in 3 instructions instead of the
+// ~13 of the generic division sequence.  The divisors on the hot path (time increments, dt, tau) are
+// shared by all envs, so r is computed once per block / thread.
+__device__ __forceinline__ float div_by(float x, float d, float r) {
+  const float q = __fmul_rn(x, r);
+  const float rem = fmaf(-q, d, x);
+  return fmaf(rem, r, q);
+}
+
 // ------------------------------------------------------------------------------------------
 // self collision (base_reacher.py:105-119, utils.py:1-9)
 // The reference tests ccw(A,B,C) = cross(B-A, C-A) > 1e-12 on joint positions.  With unit links
@@ -85,36 +95,53 @@ __device__ __forceinline__ float sin_reduced(double phi) {
 // starts straight (q = [q0,0,..,0]) where the position form would be pure rounding noise around
 // the 1e-12 threshold.  Exactly collinear links give exactly 0 -> "not ccw", as in the reference.
 // ------------------------------------------------------------------------------------------
+template <int N, bool ACCURATE>
+__device__ __forceinline__ bool self_hits(const double (&th)[N], const float (&cs)[N], const float (&sn)[N],
+                                          float& min_abs) {
+  float S[N][N];   // S[i][l] = sin(th[l]-th[i]), i<l  (fully unrolled -> registers)
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int l = i + 1; l < N; ++l)
+      S[i][l] = ACCURATE ? sin_reduced(th[l] - th[i]) : fmaf(sn[l], cs[i], -__fmul_rn(cs[l], sn[i]));
+  bool hit = false;
+  const float eps = 1e-12f;
+  min_abs = 1e30f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = i + 2; j < N; ++j) {
+      float c3 = 0.f;                       // ccw(A,B,C): l = i+1 .. j-1
+#pragma unroll
+      for (int l = i + 1; l <= j - 1; ++l) c3 += S[i][l];
+      const float c4 = c3 + S[i][j];        // ccw(A,B,D)
+      float c2 = 0.f;                       // ccw(B,C,D): l = i+1 .. j-1
+#pragma unroll
+      for (int l = j - 1; l >= i + 1; --l) c2 += S[l][j];
+      const float c1 = c2 + S[i][j];        // ccw(A,C,D): l = i .. j-1
+      hit |= ((c1 > eps) != (c2 > eps)) & ((c3 > eps) != (c4 > eps));
+      if (!ACCURATE) min_abs = fminf(fminf(min_abs, fminf(fabsf(c1), fabsf(c2))), fminf(fabsf(c3), fabsf(c4)));
+    }
+  }
+  return hit;
+}
+
+// cs / sn: float32 cos / sin of the absolute link angles th (from the forward kinematics).  The orientation
+// values are first formed from them (sin(a-b) = sin a cos b - cos a sin b, absolute error < 2e-6 on a sum);
+// unless every one of them is farther than 8e-6 from zero — i.e. unless some links are (nearly) collinear —
+// the decisions are already those of the accurate evaluation, which is only entered otherwise.
 template <int N>
-__device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N]) {
+__device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N], const float (&cs)[N],
+                                               const float (&sn)[N]) {
   bool lim = false;
 #pragma unroll
-  for (int i = 0; i < N; ++i) lim |= (q[i] > kPi) | (q[i] < -kPi);
+  for (int i = 0; i < N; ++i) lim |= fabs(q[i]) > kPi;      // any(q > pi) or any(q < -pi)
   if constexpr (N < 3) {
     return lim;
   } else {
-    float S[N][N];   // S[i][l] = sin(th[l]-th[i]), i<l  (fully unrolled -> registers)
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int l = i + 1; l < N; ++l) S[i][l] = sin_reduced(th[l] - th[i]);
-    bool hit = false;
-    const float eps = 1e-12f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-      for (int j = i + 2; j < N; ++j) {
-        float c3 = 0.f;                       // ccw(A,B,C): l = i+1 .. j-1
-#pragma unroll
-        for (int l = i + 1; l <= j - 1; ++l) c3 += S[i][l];
-        const float c4 = c3 + S[i][j];        // ccw(A,B,D)
-        float c2 = 0.f;                       // ccw(B,C,D): l = i+1 .. j-1
-#pragma unroll
-        for (int l = j - 1; l >= i + 1; --l) c2 += S[l][j];
-        const float c1 = c2 + S[i][j];        // ccw(A,C,D): l = i .. j-1
-        hit |= ((c1 > eps) != (c2 > eps)) & ((c3 > eps) != (c4 > eps));
-      }
-    }
+    float min_abs;
+    bool hit = self_hits<N, false>(th, cs, sn, min_abs);
+    if (min_abs <= 8e-6f) hit = self_hits<N, true>(th, cs, sn, min_abs);
     return lim | hit;
   }
 }

@@ -21,8 +21,9 @@ template <int MP, int N, int KW>
 cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel, float* pos_out,
                           float* vel_out, long long B, cudaStream_t stream, int max_smem_optin, int sm_count,
                           const char** why) {
-  const size_t fl = (size_t)c.T * c.cols_a + (size_t)c.rows_b * c.cols_b + (size_t)kTrajWarps * 2 * 32 * N +
-                    (KW == 0 ? (size_t)kTrajWarps * N * c.cols_a : 0);
+  auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
+  const size_t fl = (size_t)c.T * pad4(c.cols_a) + (size_t)c.rows_b * pad4(c.cols_b) + pad4(c.rows_b) +
+                    (size_t)kTrajWarps * 2 * 32 * N + (KW == 0 ? (size_t)kTrajWarps * N * c.cols_a : 0);
   const size_t smem = fl * sizeof(float);
   if (smem > (size_t)max_smem_optin) {
     *why = "tables exceed the shared memory of one SM";
@@ -33,9 +34,12 @@ cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  // persistent grid: a multiple of the SM count, each warp strides over envs
+  // persistent grid: (resident blocks per SM) x (SM count), each warp strides over envs
+  int per_sm = 1;
+  cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTrajThreads, smem);
+  if (eo != cudaSuccess) return eo;
   long long want = (B + kTrajWarps - 1) / kTrajWarps;
-  long long cap = (long long)sm_count * 8;
+  long long cap = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
   const unsigned blocks = (unsigned)(want < cap ? want : cap);
   kern<<<blocks, kTrajThreads, smem, stream>>>(c, params, bc_pos, bc_vel, pos_out, vel_out, B);
   return cudaGetLastError();

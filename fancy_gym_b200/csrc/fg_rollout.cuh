@@ -12,35 +12,51 @@ namespace fg {
 
 constexpr int kRolloutThreads = 128;
 
-// shared memory layout (floats): [tab_a T*cols_a][tab_b rows_b*cols_b][s_m 100][w  PW * blockDim]
-__host__ __device__ inline size_t rollout_smem_floats(int T, int cols_a, int rows_b, int cols_b, int pw, int threads) {
-  return (size_t)T * cols_a + (size_t)rows_b * cols_b + kLinePoints + (size_t)pw * threads;
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+
+// per-dof weight slots: ProMP K, DMP K + goal, ProDMP [y_b, tau*dy_b, w_0..w_K-1, g]
+__host__ __device__ constexpr int weight_slots(int mp, int K) {
+  return mp == FG_MP_PROMP ? K : mp == FG_MP_DMP ? K + 1 : mp == FG_MP_PRODMP ? K + 3 : 0;
 }
 
-// per-env weight slot count in shared memory
-template <int MP>
-__host__ __device__ inline int weight_slots(int n_dof, int K) {
-  if (MP == FG_MP_PROMP) return n_dof * K;
-  if (MP == FG_MP_DMP) return n_dof * (K + 1);
-  if (MP == FG_MP_PRODMP) return n_dof * (K + 3);   // [y_b, tau*dy_b, w_0..w_K-1, g]
-  return 0;
+// shared memory layout (floats):
+//   [tab_a T * pad4(cols_a)] [tab_b rows_b * pad4(cols_b)] [1/tab_b pad4(rows_b)] [s_m 100] [w  slots * n_dof * blockDim]
+__host__ __device__ inline size_t rollout_smem_floats(int T, int cols_a, int rows_b, int cols_b, int w_per_thread,
+                                                      int threads) {
+  return (size_t)T * pad4(cols_a) + (size_t)rows_b * pad4(cols_b) + pad4(rows_b) + kLinePoints +
+         (size_t)w_per_thread * threads;
 }
 
-template <int ENV, int MP, bool MOTOR, int N>
+// KC > 0: the number of weighted basis functions is a compile-time constant (the registry default 5): the per-env
+//         weights live in REGISTERS and the (float4-padded) table rows are fetched with vector broadcast loads.
+// KC == 0: run-time K; weights stay in shared memory (k-major, thread-minor: conflict free).
+template <int ENV, int MP, bool MOTOR, int N, int KC>
 __global__ void __launch_bounds__(kRolloutThreads)
 k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
           const int seg_steps) {
-  extern __shared__ float smem[];
-  const int T = c.T, K = c.K;
+  extern __shared__ __align__(16) float smem[];
+  const int T = c.T;
+  const int K = (KC > 0) ? KC : c.K;
+  const int CA = (KC > 0) ? weight_slots(MP, KC) : c.cols_a;   // table columns == weight slots per dof
+  const int RA = pad4(CA), RB = pad4(c.cols_b);
   float* tabA = smem;
-  float* tabB = tabA + T * c.cols_a;
-  float* s_m = tabB + c.rows_b * c.cols_b;
+  float* tabB = tabA + T * RA;
+  float* tabR = tabB + c.rows_b * RB;          // ProMP: reciprocals of the time increments
+  float* s_m = tabR + pad4(c.rows_b);
   float* wsm = s_m + kLinePoints;
   const int tid = threadIdx.x, BD = blockDim.x;
 
-  // ---- stage the shared tables (coalesced) ----
-  for (int i = tid; i < T * c.cols_a; i += BD) tabA[i] = c.tab_a[i];
-  for (int i = tid; i < c.rows_b * c.cols_b; i += BD) tabB[i] = c.tab_b[i];
+  // ---- stage the shared tables (coalesced reads, rows zero-padded to float4) ----
+  for (int i = tid; i < T * RA; i += BD) {
+    const int r = i / max(RA, 1), col = i - r * RA;
+    tabA[i] = (col < c.cols_a) ? c.tab_a[r * c.cols_a + col] : 0.f;
+  }
+  for (int i = tid; i < c.rows_b * RB; i += BD) {
+    const int r = i / max(RB, 1), col = i - r * RB;
+    tabB[i] = (col < c.cols_b) ? c.tab_b[r * c.cols_b + col] : 0.f;
+  }
+  if constexpr (MP == FG_MP_PROMP)
+    for (int i = tid; i < c.rows_b; i += BD) tabR[i] = __frcp_rn(c.tab_b[i]);
   for (int i = tid; i < kLinePoints; i += BD)   // float32(numpy.linspace(0,1,100)): i*(1/99) in float64, last forced to 1
     s_m[i] = (i == kLinePoints - 1) ? 1.0f : (float)((double)i * (1.0 / 99.0));
 
@@ -48,11 +64,11 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   const long long b = b0 + tid;
   const bool valid = b < B;
 
-  // ---- stage this block's MP parameters: coalesced read of [BD, P], stored k-major / thread-minor ----
+  // ---- stage this block's MP parameters: coalesced read of [BD, P], stored slot-major / thread-minor ----
   constexpr bool HAS_W = (MP != FG_MP_TRAJ);
   const int KP = (MP == FG_MP_PROMP) ? K : K + 1;         // params per dof
   const int P = N * KP;
-  const int WS = (MP == FG_MP_PRODMP) ? K + 3 : KP;       // smem slots per dof
+  const int WS = weight_slots(MP, K);                     // slots per dof
   if constexpr (HAS_W) {
     const long long nblk = min((long long)BD, B - b0);
     for (long long f = tid; f < nblk * P; f += BD) {
@@ -66,7 +82,6 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   }
   __syncthreads();
   if (!valid) return;
-#define W(d, k) wsm[((d) * WS + (k)) * BD + tid]
 
   if (io.done[b]) {   // episode already over: frozen (oracle/blackbox.py keeps such envs untouched)
     io.ret[b] = 0.0;
@@ -114,18 +129,52 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     }
   }
 
+  // ---- per-env weights: registers (KC > 0) or shared memory (KC == 0) ----
+  constexpr int WSC = (KC > 0) ? weight_slots(MP, KC) : 1;
+  constexpr int RAC = pad4(WSC) > 0 ? pad4(WSC) : 4;
+  float wreg[N][(KC > 0 && HAS_W) ? WSC : 1];
+#define WSM(d, k) wsm[((d) * WS + (k)) * BD + tid]
+  if constexpr (MP == FG_MP_PRODMP) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      WSM(d, 0) = ybc[d];
+      WSM(d, 1) = __fmul_rn(vbc[d], c.tau);
+      if (c.rel_goal) WSM(d, K + 2) = __fadd_rn(WSM(d, K + 2), ybc[d]);
+    }
+  }
+  if constexpr (KC > 0 && HAS_W) {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+      for (int k = 0; k < WSC; ++k) wreg[d][k] = WSM(d, k);
+  }
+  // dot(table row, weights of dof d): FMA chain in index order, accumulator starts at 0 (oracle 'mirror' mode)
+  auto dot_row = [&](const float* row, int d, int n) -> float {
+    float acc = 0.f;
+    if constexpr (KC > 0) {
+      float r[RAC];
+#pragma unroll
+      for (int j = 0; j < RAC / 4; ++j) {
+        const float4 x = reinterpret_cast<const float4*>(row)[j];
+        r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
+      }
+#pragma unroll
+      for (int k = 0; k < WSC; ++k)
+        if (k < n) acc = fmaf(r[k], wreg[d][k], acc);
+    } else {
+      for (int k = 0; k < n; ++k) acc = fmaf(row[k], WSM(d, k), acc);
+    }
+    return acc;
+  };
+  auto weight = [&](int d, int k) -> float {
+    if constexpr (KC > 0) return wreg[d][k]; else return WSM(d, k);
+  };
+
   // ---- MP set-up ----
   float dmp_y[N], dmp_yd[N];        // DMP integrator state (scaled-time velocity)
   float pos_next[N];                // ProMP: pos[t+1] carried to the next step
   float vel_prev[N];
-  if constexpr (MP == FG_MP_PRODMP) {
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-      W(d, 0) = ybc[d];
-      W(d, 1) = __fmul_rn(vbc[d], c.tau);
-      if (c.rel_goal) W(d, K + 2) = __fadd_rn(W(d, K + 2), ybc[d]);
-    }
-  }
+  const float r_tau = __frcp_rn(c.tau), r_dt = __frcp_rn(c.dt_f);
   if constexpr (MP == FG_MP_DMP) {
 #pragma unroll
     for (int d = 0; d < N; ++d) {
@@ -136,9 +185,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   if constexpr (MP == FG_MP_PROMP) {
 #pragma unroll
     for (int d = 0; d < N; ++d) {
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k) acc = fmaf(tabA[k], W(d, k), acc);
-      pos_next[d] = acc;
+      pos_next[d] = dot_row(tabA, d, K);
       vel_prev[d] = 0.f;
     }
   }
@@ -155,14 +202,13 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
       for (int d = 0; d < N; ++d) pos[d] = pos_next[d];
       if (t < T - 1) {
-        const float* row = tabA + (t + 1) * K;
-        const float dtt = tabB[t];
+        const float* row = tabA + (t + 1) * RA;
+        const float dtt = tabB[t * RB], rdt = tabR[t];
 #pragma unroll
         for (int d = 0; d < N; ++d) {
-          float acc = 0.f;
-          for (int k = 0; k < K; ++k) acc = fmaf(row[k], W(d, k), acc);
+          const float acc = dot_row(row, d, K);
           pos_next[d] = acc;
-          vel[d] = __fdiv_rn(__fsub_rn(acc, pos[d]), dtt);
+          vel[d] = div_by(__fsub_rn(acc, pos[d]), dtt, rdt);     // (pos[t+1]-pos[t]) / (times[t+1]-times[t])
           vel_prev[d] = vel[d];
         }
       } else {
@@ -173,16 +219,15 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
       for (int d = 0; d < N; ++d) {
         pos[d] = dmp_y[d];
-        vel[d] = __fdiv_rn(dmp_yd[d], c.tau);
+        vel[d] = div_by(dmp_yd[d], c.tau, r_tau);
       }
       if (t < T - 1) {   // semi-implicit Euler in scaled time (oracle/mp.py DMP._integrate)
-        const float* row = tabA + t * K;
-        const float h = tabB[t];
+        const float* row = tabA + t * RA;
+        const float h = tabB[t * RB];
 #pragma unroll
         for (int d = 0; d < N; ++d) {
-          float f = 0.f;
-          for (int k = 0; k < K; ++k) f = fmaf(row[k], W(d, k), f);
-          const float g = W(d, K);
+          const float f = dot_row(row, d, K);
+          const float g = weight(d, K);
           float a = __fmul_rn(c.beta, __fsub_rn(g, dmp_y[d]));
           a = __fmul_rn(c.alpha, __fsub_rn(a, dmp_yd[d]));
           a = __fadd_rn(a, f);
@@ -191,18 +236,12 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
         }
       }
     } else if constexpr (MP == FG_MP_PRODMP) {
-      const float* rp = tabA + t * (K + 3);
-      const float* rv = tabB + t * (K + 3);
+      const float* rp = tabA + t * RA;
+      const float* rv = tabB + t * RB;
 #pragma unroll
       for (int d = 0; d < N; ++d) {
-        float ap = 0.f, av = 0.f;
-        for (int k = 0; k < K + 3; ++k) {
-          const float w = W(d, k);
-          ap = fmaf(rp[k], w, ap);
-          av = fmaf(rv[k], w, av);
-        }
-        pos[d] = ap;
-        vel[d] = __fdiv_rn(av, c.tau);
+        pos[d] = dot_row(rp, d, K + 3);
+        vel[d] = div_by(dot_row(rv, d, K + 3), c.tau, r_tau);
       }
     } else {
 #pragma unroll
@@ -215,7 +254,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     // ------------------------------------------------------------------ controller + clip + dynamics
     double a64[N];
     float a32[N];
-    double acc_cost = 0.0;    // sum(acc^2) (direct envs) / sum(a^2) as the reference's dtype dictates
+    double acc_cost = 0.0;    // sum(acc^2) (direct envs), in the reference's dtype
     if constexpr (MOTOR) {    // pd_controller.py:28: float64 because c_pos / c_vel are float64
 #pragma unroll
       for (int i = 0; i < N; ++i) {
@@ -243,7 +282,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
         float s32 = 0.f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const float ac = __fdiv_rn(__fsub_rn(a32[i], (float)v[i]), c.dt_f);
+          const float ac = div_by(__fsub_rn(a32[i], (float)v[i]), c.dt_f, r_dt);
           s32 = __fadd_rn(s32, __fmul_rn(ac, ac));
         }
         acc_cost = (double)s32;
@@ -273,14 +312,12 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       for (int i = 1; i < N; ++i) th[i] = th[i - 1] + q[i];
 
       if constexpr (ENV == FG_ENV_HOLE_REACHER) {
-        bool selfc = false, wallc = false;
-        if (!c.allow_self) selfc = self_collision<N>(q, th);
-        if (!c.allow_wall) {
-          float cs[N], sn[N];
+        float cs[N], sn[N];
 #pragma unroll
-          for (int i = 0; i < N; ++i) sincos_reduced(th[i], sn[i], cs[i]);
-          wallc = wall_collision<N>(s_m, cs, sn, hole, c.wall_mode);
-        }
+        for (int i = 0; i < N; ++i) sincos_reduced(th[i], sn[i], cs[i]);
+        bool selfc = false, wallc = false;
+        if (!c.allow_self) selfc = self_collision<N>(q, th, cs, sn);
+        if (!c.allow_wall) wallc = wall_collision<N>(s_m, cs, sn, hole, c.wall_mode);
         collided = selfc | wallc;
         // hr_simple_reward.py:35-53
         double dist_cost = 0.0, coll_cost = 0.0;
@@ -299,7 +336,13 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
         terminated = collided;
       } else if constexpr (ENV == FG_ENV_VIAPOINT_REACHER) {
         // viapoint_reacher.py:79-107 (App. A.6-Q1/Q2: -inf start, `acc` is the action)
-        collided = c.allow_self ? false : self_collision<N>(q, th);
+        collided = false;
+        if (!c.allow_self) {
+          float cs[N], sn[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) sincos_reduced(th[i], sn[i], cs[i]);
+          collided = self_collision<N>(q, th, cs, sn);
+        }
         double dist = INFINITY;
         reward = -INFINITY;
         success = false;
@@ -318,9 +361,8 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
           reward = -c.penalty;
         }
         reward -= dist * dist;
-        double asq;
         if constexpr (MOTOR) {
-          asq = 0.0;
+          double asq = 0.0;
 #pragma unroll
           for (int i = 0; i < N; ++i) asq += a64[i] * a64[i];
           reward -= 5e-8 * asq;
@@ -439,7 +481,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   io.info[b * 4 + 1] = info1;
   io.info[b * 4 + 2] = 0.0;
   io.info[b * 4 + 3] = 0.0;
-#undef W
+#undef WSM
 }
 
 }  // namespace fg

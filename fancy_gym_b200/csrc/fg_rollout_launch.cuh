@@ -5,19 +5,16 @@
 
 namespace fg {
 
-template <int ENV, int MP, bool MOTOR, int N>
-cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                       int max_smem_optin, const char** why) {
-  int pw = 0;
-  if (MP == FG_MP_PROMP) pw = weight_slots<FG_MP_PROMP>(N, c.K);
-  if (MP == FG_MP_DMP) pw = weight_slots<FG_MP_DMP>(N, c.K);
-  if (MP == FG_MP_PRODMP) pw = weight_slots<FG_MP_PRODMP>(N, c.K);
+template <int ENV, int MP, bool MOTOR, int N, int KC>
+cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
+                      int max_smem_optin, const char** why) {
+  const int pw = N * weight_slots(MP, c.K);
   const size_t smem = sizeof(float) * rollout_smem_floats(c.T, c.cols_a, c.rows_b, c.cols_b, pw, kRolloutThreads);
   if (smem > (size_t)max_smem_optin) {
     *why = "tables + per-thread weights exceed the shared memory of one SM (reduce n_steps or n_basis)";
     return cudaSuccess;
   }
-  auto kern = k_rollout<ENV, MP, MOTOR, N>;
+  auto kern = k_rollout<ENV, MP, MOTOR, N, KC>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -25,6 +22,16 @@ cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, in
   const long long blocks = (B + kRolloutThreads - 1) / kRolloutThreads;
   kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, io, B, seg_steps);
   return cudaGetLastError();
+}
+
+template <int ENV, int MP, bool MOTOR, int N>
+cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
+                       int max_smem_optin, const char** why) {
+  // num_basis = 5 is the registry default of every MP type (registry.py:76-125): register-resident weights
+  if constexpr (MP != FG_MP_TRAJ) {
+    if (c.K == 5) return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why);
+  }
+  return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why);
 }
 
 template <int ENV, int N>

@@ -113,23 +113,55 @@ def _cross(A, B, C):
     return (C[:, 1] - A[:, 1]) * (B[:, 0] - A[:, 0]) - (B[:, 1] - A[:, 1]) * (C[:, 0] - A[:, 0])
 
 
-def self_collision(q, J, allow_self_collision=False):
+def self_collision(q, J, allow_self_collision=False, margins=True):
     """base_reacher/base_reacher.py:105-119 + utils.py:1-9.
-    Returns (collided [B] bool, margin [B]): margin = min distance of any tested quantity to
-    its threshold (|q|-pi for the joint limits, |cross-1e-12| for every orientation test)."""
+    Returns (collided [B] bool, margin [B]).
+
+    margin: how far the decision is from flipping, in the error model of a float32 evaluation.
+    Every orientation test value is (in exact arithmetic) a sum of sines of relative link angles,
+      ccw(J_i,J_i+1,J_m) = sum_{l=i+1}^{m-1} sin(th_l - th_i),  ccw(J_a,J_j,J_j+1) = sum_{l=a}^{j-1} sin(th_j - th_l),
+    so a float32 evaluation has an error *relative* to sum |sin|; the margin of one test is
+    |value - 1e-12| / sum|sin| (inf when all its terms vanish: exactly collinear links are decided
+    identically by both sides).  Per link pair the margin is what it takes to flip `intersect`
+    (both XORs must hold: max of the two "needs" when it is False, min of the two "breaks" when True);
+    the joint-limit margin |q| - pi is absolute (q itself is bit-identical on both sides)."""
     B, n = q.shape
     if allow_self_collision:
         return np.zeros(B, bool), np.full(B, np.inf)
     limit = np.any(q > np.pi, axis=1) | np.any(q < -np.pi, axis=1)
-    margin = np.min(np.abs(np.abs(q) - np.pi), axis=1)
     hit = np.zeros(B, bool)
+    if not margins:     # decision only, exactly the reference's arithmetic
+        for i in range(n):
+            for j in range(i + 2, n):
+                A, Bp, C, D = J[:, i], J[:, i + 1], J[:, j], J[:, j + 1]
+                hit |= ((_cross(A, C, D) > CCW_EPS) != (_cross(Bp, C, D) > CCW_EPS)) & \
+                       ((_cross(A, Bp, C) > CCW_EPS) != (_cross(A, Bp, D) > CCW_EPS))
+        return limit | hit, np.full(B, np.inf)
+    margin = np.min(np.abs(np.abs(q) - np.pi), axis=1)
+    th = np.cumsum(q, axis=1)
+    absin = np.abs(np.sin(th[:, None, :] - th[:, :, None]))       # [B, i, l] = |sin(th_l - th_i)|
+
+    def rel(c, scale):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(scale > 0, np.abs(c - CCW_EPS) / scale, np.inf)
+
     for i in range(n):
         for j in range(i + 2, n):
             A, Bp, C, D = J[:, i], J[:, i + 1], J[:, j], J[:, j + 1]
             c1, c2, c3, c4 = _cross(A, C, D), _cross(Bp, C, D), _cross(A, Bp, C), _cross(A, Bp, D)
-            hit |= ((c1 > CCW_EPS) != (c2 > CCW_EPS)) & ((c3 > CCW_EPS) != (c4 > CCW_EPS))
-            for c in (c1, c2, c3, c4):
-                margin = np.minimum(margin, np.abs(c - CCW_EPS))
+            x12 = (c1 > CCW_EPS) != (c2 > CCW_EPS)
+            x34 = (c3 > CCW_EPS) != (c4 > CCW_EPS)
+            pair_hit = x12 & x34
+            hit |= pair_hit
+            s3 = absin[:, i, i + 1:j].sum(axis=1)
+            s4 = s3 + absin[:, i, j]
+            s2 = absin[:, i + 1:j, j].sum(axis=1)
+            s1 = s2 + absin[:, i, j]
+            m12 = np.minimum(rel(c1, s1), rel(c2, s2))       # perturbation that flips XOR(c1, c2)
+            m34 = np.minimum(rel(c3, s3), rel(c4, s4))
+            need = np.maximum(np.where(x12, 0.0, m12), np.where(x34, 0.0, m34))
+            brk = np.minimum(m12, m34)
+            margin = np.minimum(margin, np.where(pair_hit, brk, need))
     return limit | hit, margin
 
 
@@ -152,7 +184,7 @@ def line_points(q):
     return pts
 
 
-def wall_collision(q, hole_x, hole_w, hole_d, allow_wall_collision=False):
+def wall_collision(q, hole_x, hole_w, hole_d, allow_wall_collision=False, margins=True):
     """hole_reacher/hole_reacher.py:148-179 (check_wall_collision).
     Returns (collided [B], margin [B]).  margin: for a free state the L-inf distance of the
     nearest sampled point to the forbidden region; for a colliding state the largest L-inf
@@ -162,6 +194,8 @@ def wall_collision(q, hole_x, hole_w, hole_d, allow_wall_collision=False):
         return np.zeros(B, bool), np.full(B, np.inf)
     pts = line_points(q).reshape(B, -1, 2)
     px, py = pts[:, :, 0], pts[:, :, 1]
+    # (sample 0 of link 0 is the arm base, exactly (0, 0) on both sides: it sits on the region boundary by
+    # construction and is excluded from the margin, not from the decision)
     xl = (hole_x - hole_w / 2)[:, None]
     xr = (hole_x + hole_w / 2)[:, None]
     d = hole_d[:, None]
@@ -170,11 +204,13 @@ def wall_collision(q, hole_x, hole_w, hole_d, allow_wall_collision=False):
     r3 = (px > xl) & (px < xr) & (py < -d)
     inside = r1 | r2 | r3
     hit = inside.any(axis=1)
+    if not margins:
+        return hit, np.full(B, np.inf)
     pos = lambda a: np.maximum(a, 0.0)   # noqa: E731
     dist1 = np.maximum(pos(px - xl), pos(py))
     dist2 = np.maximum(pos(xr - px), pos(py))
     dist3 = np.maximum(np.maximum(pos(xl - px), pos(px - xr)), pos(py + d))
-    free_margin = np.minimum(np.minimum(dist1, dist2), dist3).min(axis=1)
+    free_margin = np.minimum(np.minimum(dist1, dist2), dist3)[:, 1:].min(axis=1)
     depth1 = np.minimum(xl - px, -py)
     depth2 = np.minimum(px - xr, -py)
     depth3 = np.minimum(np.minimum(px - xl, xr - px), -d - py)
@@ -212,6 +248,8 @@ class BatchedReacher:
         if kind == "hole" and rew_fct != "simple":
             raise NotImplementedError("oracle restates rew_fct='simple' (the -v0 registration)")
         self.dt = DT
+        self.compute_margins = True     # bench.py's CPU baseline switches the (non-reference) margin bookkeeping off
+        self.double_collision_eval = False   # ... and evaluates the collision tests twice per step like the reference (App. A.6-Q3)
         self.torque = kind == "simple"
         # action bounds: base_reacher_direct.py:16-18 (2*pi), base_reacher_torque.py:16-18 (1000);
         # Box default dtype float32
@@ -309,10 +347,15 @@ class BatchedReacher:
             self.q = self.q + self.dt * self.v
         self.J = forward_kinematics(self.q)
 
-        selfc, margin = self_collision(self.q, self.J, self.allow_self_collision)
+        mg = self.compute_margins
+        selfc, margin = self_collision(self.q, self.J, self.allow_self_collision, mg)
+        if self.kind != "simple" and self.double_collision_eval:   # the reference evaluates the tests again in the reward (Q3)
+            self_collision(self.q, self.J, self.allow_self_collision, mg)
         if self.kind == "hole":
             wallc, wmargin = wall_collision(self.q, self.hole_x, self.hole_w, self.hole_d,
-                                            self.allow_wall_collision)
+                                            self.allow_wall_collision, mg)
+            if self.double_collision_eval:
+                wall_collision(self.q, self.hole_x, self.hole_w, self.hole_d, self.allow_wall_collision, mg)
             collided = selfc | wallc
             margin = np.minimum(margin, wmargin)
             reward, info = self._reward_hole(collided)
