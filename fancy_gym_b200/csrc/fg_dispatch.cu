@@ -22,8 +22,9 @@ cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_
                           float* vel_out, long long B, cudaStream_t stream, int max_smem_optin, int sm_count,
                           const char** why) {
   auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
-  const size_t fl = (size_t)c.T * pad4(c.cols_a) + (size_t)c.rows_b * pad4(c.cols_b) + pad4(c.rows_b) +
-                    (size_t)kTrajWarps * 2 * 32 * N + (KW == 0 ? (size_t)kTrajWarps * N * c.cols_a : 0);
+  const int RA = traj_row_stride(c.cols_a), RB = (MP == FG_MP_PROMP) ? 1 : RA;
+  const size_t fl = (size_t)kTrajWarps * 2 * kTrajStageFloats + (size_t)c.T * RA + pad4(c.rows_b * RB) + pad4(c.rows_b) +
+                    (KW == 0 ? (size_t)kTrajWarps * N * c.cols_a : 0);
   const size_t smem = fl * sizeof(float);
   if (smem > (size_t)max_smem_optin) {
     *why = "tables exceed the shared memory of one SM";

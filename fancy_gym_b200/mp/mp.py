@@ -150,7 +150,9 @@ class MPInterface:
             self._handles[key] = h
         return h
 
-    def _run_trajgen(self):
+    def _run_trajgen(self, out=None):
+        """Launches fg_trajgen for the current params / plan.  `out=(pos, vel)` re-uses caller-owned
+        [B, T, dof] float32 device buffers (no allocation on the call path)."""
         if self.params is None:
             raise RuntimeError("set_params() must be called before get_traj_pos()/get_traj_vel()")
         p = self.params.to(self.device, torch.float32)
@@ -167,8 +169,12 @@ class MPInterface:
             return x.expand(B, N).contiguous() if x.dim() < 2 else x.contiguous()
 
         bp, bv = bc(self.init_pos), bc(self.init_vel)
-        pos = torch.empty(B, T, N, device=self.device, dtype=torch.float32)
-        vel = torch.empty_like(pos)
+        if out is None:
+            pos = torch.empty(B, T, N, device=self.device, dtype=torch.float32)
+            vel = torch.empty_like(pos)
+        else:
+            pos, vel = out
+            assert pos.shape == (B, T, N) and vel.shape == (B, T, N) and pos.is_contiguous() and vel.is_contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib.fg_trajgen(self._trajgen_handle(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
                                        bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(), B,
