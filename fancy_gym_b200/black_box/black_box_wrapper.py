@@ -21,10 +21,8 @@ import torch
 from .. import _lib
 from ..mp import MPInterface
 from ..utils.gym_compat import Box, Wrapper
-from .controller import BaseController, PDController, PosController, VelController
+from .controller import BaseController
 from .raw_interface_wrapper import RawInterfaceWrapper
-
-_CTRL_KIND = {"velocity": _lib.CTRL_VELOCITY, "position": _lib.CTRL_POSITION, "motor": _lib.CTRL_MOTOR}
 
 
 class BlackBoxWrapper(Wrapper):
@@ -127,14 +125,12 @@ class BlackBoxWrapper(Wrapper):
     # ---- kernel handle for the current plan -----------------------------------------------------
     def _controller_cfg(self, cfg):
         ctrl = self.tracking_controller
-        kind = getattr(ctrl, "kind", None)
-        if kind not in _CTRL_KIND:
+        code = getattr(ctrl, "abi_code", None)
+        if code is None:
             raise NotImplementedError(f"controller {type(ctrl).__name__} is not available inside the fused kernel")
-        cfg.ctrl_kind = _CTRL_KIND[kind]
-        n = self._base.n_links
-        p = np.broadcast_to(np.asarray(getattr(ctrl, "p_gains", 0.0), dtype=np.float64), (n,))
-        d = np.broadcast_to(np.asarray(getattr(ctrl, "d_gains", 0.0), dtype=np.float64), (n,))
-        for i in range(n):
+        cfg.ctrl_kind = code
+        p, d = ctrl.gain_vectors(self._base.n_links)
+        for i in range(self._base.n_links):
             cfg.p_gains[i], cfg.d_gains[i] = float(p[i]), float(d[i])
 
     def _handle(self):

@@ -1,20 +1,20 @@
-from ...mp import (ExpDecayPhaseGenerator, NormalizedRBFBasisGenerator, PhaseGenerator, ProDMPBasisGenerator,
-                   ZeroPaddingNormalizedRBFBasisGenerator)
+"""basis_generator_type -> basis generator (fancy_gym/black_box/factory/basis_generator_factory.py:5-23);
+`prodmp` insists on an exponential-decay phase, `rhythmic` is reserved."""
+from ... import mp
+from ._select import TypeSelector
 
-ALL_TYPES = ["rbf", "zero_rbf", "rhythmic"]
+
+def _needs_exp_phase(phase_generator, **_):
+    assert isinstance(phase_generator, mp.ExpDecayPhaseGenerator)
 
 
-def get_basis_generator(basis_generator_type: str, phase_generator: PhaseGenerator, **kwargs):
-    """fancy_gym/black_box/factory/basis_generator_factory.py:8-23"""
-    basis_generator_type = basis_generator_type.lower()
-    if basis_generator_type == "rbf":
-        return NormalizedRBFBasisGenerator(phase_generator, **kwargs)
-    elif basis_generator_type == "zero_rbf":
-        return ZeroPaddingNormalizedRBFBasisGenerator(phase_generator, **kwargs)
-    elif basis_generator_type == "prodmp":
-        assert isinstance(phase_generator, ExpDecayPhaseGenerator)
-        return ProDMPBasisGenerator(phase_generator, **kwargs)
-    elif basis_generator_type == "rhythmic":
-        raise NotImplementedError()
-    raise ValueError(f"Specified basis generator type {basis_generator_type} not supported, "
-                     f"please choose one of {ALL_TYPES}.")
+_SELECT = TypeSelector("basis generator",
+                       {"rbf": mp.NormalizedRBFBasisGenerator, "zero_rbf": mp.ZeroPaddingNormalizedRBFBasisGenerator,
+                        "prodmp": mp.ProDMPBasisGenerator},
+                       reserved=("rhythmic",), advertised=["rbf", "zero_rbf", "rhythmic"],
+                       requires={"prodmp": _needs_exp_phase})
+ALL_TYPES = _SELECT.advertised
+
+
+def get_basis_generator(basis_generator_type: str, phase_generator, **kwargs):
+    return _SELECT.build(basis_generator_type, phase_generator, **kwargs)

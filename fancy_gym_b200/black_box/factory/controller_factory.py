@@ -1,18 +1,11 @@
-from ..controller import MetaWorldController, PDController, PosController, VelController
+"""controller_type -> tracking law (fancy_gym/black_box/factory/controller_factory.py:6-21)."""
+from ..controller import laws
+from ._select import TypeSelector
 
-ALL_TYPES = ["motor", "velocity", "position", "metaworld"]
+_SELECT = TypeSelector("controller", {"motor": laws.PDController, "velocity": laws.VelController,
+                                      "position": laws.PosController, "metaworld": laws.MetaWorldController})
+ALL_TYPES = _SELECT.advertised
 
 
 def get_controller(controller_type: str, **kwargs):
-    """fancy_gym/black_box/factory/controller_factory.py:9-21"""
-    controller_type = controller_type.lower()
-    if controller_type == "motor":
-        return PDController(**kwargs)
-    elif controller_type == "velocity":
-        return VelController(**kwargs)
-    elif controller_type == "position":
-        return PosController(**kwargs)
-    elif controller_type == "metaworld":
-        return MetaWorldController(**kwargs)
-    raise ValueError(f"Specified controller type {controller_type} not supported, "
-                     f"please choose one of {ALL_TYPES}.")
+    return _SELECT.build(controller_type, **kwargs)

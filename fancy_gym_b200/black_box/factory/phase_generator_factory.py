@@ -1,16 +1,12 @@
-from ...mp import ExpDecayPhaseGenerator, LinearPhaseGenerator
+"""phase_generator_type -> phase generator (fancy_gym/black_box/factory/phase_generator_factory.py:6-23);
+`rhythmic` and `smooth` are reserved names there and raise NotImplementedError."""
+from ... import mp
+from ._select import TypeSelector
 
-ALL_TYPES = ["linear", "exp", "rhythmic", "smooth"]
+_SELECT = TypeSelector("phase generator", {"linear": mp.LinearPhaseGenerator, "exp": mp.ExpDecayPhaseGenerator},
+                       reserved=("rhythmic", "smooth"), advertised=["linear", "exp", "rhythmic", "smooth"])
+ALL_TYPES = _SELECT.advertised
 
 
 def get_phase_generator(phase_generator_type, **kwargs):
-    """fancy_gym/black_box/factory/phase_generator_factory.py:9-23"""
-    phase_generator_type = phase_generator_type.lower()
-    if phase_generator_type == "linear":
-        return LinearPhaseGenerator(**kwargs)
-    elif phase_generator_type == "exp":
-        return ExpDecayPhaseGenerator(**kwargs)
-    elif phase_generator_type in ("rhythmic", "smooth"):
-        raise NotImplementedError()
-    raise ValueError(f"Specified phase generator type {phase_generator_type} not supported, "
-                     f"please choose one of {ALL_TYPES}.")
+    return _SELECT.build(phase_generator_type, **kwargs)

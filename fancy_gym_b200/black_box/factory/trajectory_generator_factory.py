@@ -1,17 +1,17 @@
-from ...mp import DMP, ProDMP, ProDMPBasisGenerator, ProMP
+"""trajectory_generator_type -> MP (fancy_gym/black_box/factory/trajectory_generator_factory.py:4-21);
+`prodmp` insists on a ProDMP basis generator."""
+from ... import mp
+from ._select import TypeSelector
 
-ALL_TYPES = ["promp", "dmp", "idmp"]
+
+def _needs_prodmp_basis(basis_generator, *_, **__):
+    assert isinstance(basis_generator, mp.ProDMPBasisGenerator)
+
+
+_SELECT = TypeSelector("movement primitive", {"promp": mp.ProMP, "dmp": mp.DMP, "prodmp": mp.ProDMP},
+                       advertised=["promp", "dmp", "idmp"], requires={"prodmp": _needs_prodmp_basis})
+ALL_TYPES = _SELECT.advertised
 
 
 def get_trajectory_generator(trajectory_generator_type: str, action_dim: int, basis_generator, **kwargs):
-    """fancy_gym/black_box/factory/trajectory_generator_factory.py:7-21"""
-    trajectory_generator_type = trajectory_generator_type.lower()
-    if trajectory_generator_type == "promp":
-        return ProMP(basis_generator, action_dim, **kwargs)
-    elif trajectory_generator_type == "dmp":
-        return DMP(basis_generator, action_dim, **kwargs)
-    elif trajectory_generator_type == "prodmp":
-        assert isinstance(basis_generator, ProDMPBasisGenerator)
-        return ProDMP(basis_generator, action_dim, **kwargs)
-    raise ValueError(f"Specified movement primitive type {trajectory_generator_type} not supported, "
-                     f"please choose one of {ALL_TYPES}.")
+    return _SELECT.build(trajectory_generator_type, basis_generator, action_dim, **kwargs)
