@@ -1,0 +1,78 @@
+"""Multi-GPU layout of the rollout path: episodes are independent, so the env batch
+is cut into contiguous shards, one per rank (one process per GPU), with NO collective on the data
+path.  The only exchange is the gather of per-episode results after a black-box step.
+
+`torch.distributed` is the plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+#: columns of the packed per-episode result row
+RESULT_COLUMNS = ("return", "trajectory_length", "flags")
+
+
+def shard_bounds(total_envs: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) of the contiguous env block owned by `rank`; the first `total % world` ranks get one extra env."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    if total_envs < 0:
+        raise ValueError("total_envs must be >= 0")
+    base, extra = divmod(total_envs, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(total_envs: int, world_size: int):
+    return [shard_bounds(total_envs, world_size, r)[1] - shard_bounds(total_envs, world_size, r)[0]
+            for r in range(world_size)]
+
+
+def pack_results(ret: torch.Tensor, length: torch.Tensor, flags: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """[B, 3] float64 rows (return, length, flags) — one buffer so that a step needs ONE collective.
+    float64 keeps returns exact (they are float64 sums) and represents lengths / flag bytes exactly."""
+    B = ret.shape[0]
+    if out is None:
+        out = torch.empty(B, 3, dtype=torch.float64, device=ret.device)
+    out[:, 0] = ret
+    out[:, 1] = length
+    out[:, 2] = flags
+    return out
+
+
+def unpack_results(packed: torch.Tensor):
+    return packed[:, 0], packed[:, 1].to(torch.int32), packed[:, 2].to(torch.uint8)
+
+
+def gather_episode_results(ret, length, flags, total_envs: Optional[int] = None, group=None,
+                           packed: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """All-gathers the per-episode results of every rank to every rank, in global env order.
+
+    Even shards use one `all_gather_into_tensor` (a single NCCL ring / NVLS op on the GPUs); ragged shards
+    (total_envs not divisible by the world size) pad to the largest shard.  Returns (ret[total], length[total],
+    flags[total]).  Without an initialised process group (single GPU) this is the identity.
+    """
+    if not (dist.is_available() and dist.is_initialized()):
+        return ret, length, flags
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B = ret.shape[0]
+    if total_envs is None:
+        total_envs = B * world
+    sizes = shard_sizes(total_envs, world)
+    if sizes[rank] != B:
+        raise ValueError(f"rank {rank} holds {B} envs, layout says {sizes[rank]}")
+    width = max(sizes)
+    packed = pack_results(ret, length, flags, out=packed)
+    if width != B:
+        padded = packed.new_zeros(width, 3)
+        padded[:B] = packed
+        packed = padded
+    if out is None:
+        out = packed.new_empty(world * width, 3)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    if min(sizes) != width:
+        out = torch.cat([out[r * width:r * width + sizes[r]] for r in range(world)], dim=0)
+    return unpack_results(out)
