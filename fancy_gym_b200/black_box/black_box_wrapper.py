@@ -70,6 +70,7 @@ class BlackBoxWrapper(Wrapper):
         self.max_planning_times = max_planning_times
         self.plan_steps = 0
         self.wall_mode = int(wall_mode)
+        self._interface_checked = False
 
         # ---- device side ----
         base = self.env.unwrapped
@@ -152,7 +153,7 @@ class BlackBoxWrapper(Wrapper):
         cfg.allow_self_collision = int(bool(getattr(base, "allow_self_collision", False)))
         cfg.allow_wall_collision = int(bool(getattr(base, "allow_wall_collision", False)))
         cfg.collision_penalty = float(getattr(base, "collision_penalty", 0.0))
-        cfg.rew_fct = 0
+        cfg.rew_fct = int(getattr(base, "rew_fct_code", 0))
         cfg.wall_mode = self.wall_mode
         cfg.time_aware = int(self._time_aware())
         idx = self._obs_index()
@@ -208,7 +209,16 @@ class BlackBoxWrapper(Wrapper):
             a = torch.minimum(torch.maximum(a, self._lo), self._hi)     # np.clip to the tau / delay bounds (:104-105)
         return a.contiguous(), as_numpy, scalar
 
+    def _require_local_state(self):
+        """The MP boundary condition is the env's current position / velocity (black_box_wrapper.py:110-111): a wrapper
+        stack that does not expose them fails on the first step, like the reference (NotImplementedError from
+        RawInterfaceWrapper.current_pos).  Checked once; the kernel reads the state buffers directly."""
+        if not self._interface_checked:
+            self.env.current_pos, self.env.current_vel   # noqa: B018  (raises if missing)
+            self._interface_checked = True
+
     def _set_plan(self, params):
+        self._require_local_state()
         tg = self.traj_gen
         duration = self.duration
         if self.learn_sub_trajectories:
@@ -243,6 +253,8 @@ class BlackBoxWrapper(Wrapper):
             io.dbg_rewards = dbg["rewards"].data_ptr()
             if "actions" in dbg:
                 io.dbg_actions = dbg["actions"].data_ptr()
+            if "obs" in dbg:
+                io.dbg_obs = dbg["obs"].data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(T if seg_steps is None else seg_steps), C.c_void_p(stream)))
 
@@ -261,6 +273,8 @@ class BlackBoxWrapper(Wrapper):
             dbg = dict(rewards=torch.zeros(B, T, dtype=torch.float64, device=self.device))
             if self.verbose >= 2:
                 dbg["actions"] = torch.zeros(B, T, n, dtype=torch.float64, device=self.device)
+                dbg["obs"] = torch.zeros(B, T, self.env.observation_space.shape[0], dtype=torch.float32, device=self.device)
+        planned = self._planned_trajectory(local) if self.verbose >= 2 else None   # before the state moves on
         self.launch(local, seg, replan_break, dbg)
         if self.condition_on_desired:
             self.condition_set = True      # every live env breaks at the same step or is done
@@ -278,6 +292,8 @@ class BlackBoxWrapper(Wrapper):
             infos["is_success"] = (flags & _lib.FLAG_SUCCESS) != 0
             infos["is_collided"] = (flags & _lib.FLAG_COLLIDED) != 0
             infos["end_effector"] = self._info[:, 0:2].clone()
+            if getattr(base, "rew_fct", None) == "unbounded":        # hr_unbounded_reward.py:53-56
+                infos["joints"] = base.q.clone()
         elif base.env_kind == _lib.ENV_SIMPLE_REACHER:
             infos["reward_dist"] = self._info[:, 0].clone()
             infos["reward_ctrl"] = self._info[:, 1].clone()
@@ -287,9 +303,9 @@ class BlackBoxWrapper(Wrapper):
             ret = torch.as_tensor(np.array([self.reward_aggregation(r[b, :ln[b]]) if ln[b] else 0.0 for b in range(B)]),
                                   device=self.device)
         if self.verbose >= 2:
-            pos, vel = self._planned_trajectory(local)
-            infos["positions"], infos["velocities"] = pos, vel
+            infos["positions"], infos["velocities"] = planned
             infos["step_actions"] = dbg["actions"]
+            infos["step_observations"] = dbg["obs"]
             infos["step_rewards"] = dbg["rewards"]
         infos["trajectory_length"] = length
         obs = self._obs.clone()
@@ -299,9 +315,9 @@ class BlackBoxWrapper(Wrapper):
         tg = self.traj_gen
         saved = tg.params
         tg.params = local_params
-        if self.condition_set and self.plan_steps > 1:
+        if self.condition_set:
             tg.set_initial_conditions(tg.init_time, self._cond_pos, self._cond_vel)
-        pos, vel = tg.get_traj_pos(), tg.get_traj_vel()
+        pos, vel = tg._run_trajgen()
         tg.params = saved
         return pos, vel
 

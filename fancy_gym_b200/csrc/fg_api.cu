@@ -55,8 +55,8 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
   if (cfg->mp_kind != FG_MP_TRAJ && (cfg->n_basis < 1 || !cfg->tab_a || !cfg->tab_b))
     return fail(FG_ERR_INVALID, "n_basis >= 1 and both tables are required for mp_kind %d", cfg->mp_kind);
   if (cfg->n_obs_out < 0 || cfg->n_obs_out > FG_MAX_OBS) return fail(FG_ERR_INVALID, "n_obs_out %d out of range", cfg->n_obs_out);
-  if (cfg->env_kind == FG_ENV_HOLE_REACHER && cfg->rew_fct != 0)
-    return fail(FG_ERR_UNSUPPORTED, "hole reacher rew_fct %d not implemented (only 'simple')", cfg->rew_fct);
+  if (cfg->env_kind == FG_ENV_HOLE_REACHER && (cfg->rew_fct < 0 || cfg->rew_fct > 2))
+    return fail(FG_ERR_INVALID, "hole reacher rew_fct %d unknown (0 simple, 1 vel_acc, 2 unbounded)", cfg->rew_fct);
 
   fg_handle* h = new (std::nothrow) fg_handle();
   if (!h) return fail(FG_ERR_NOMEM, "out of host memory");

@@ -30,7 +30,8 @@ __host__ __device__ inline size_t rollout_smem_floats(int T, int cols_a, int row
 // KC > 0: the number of weighted basis functions is a compile-time constant (the registry default 5): the per-env
 //         weights live in REGISTERS and the (float4-padded) table rows are fetched with vector broadcast loads.
 // KC == 0: run-time K; weights stay in shared memory (k-major, thread-minor: conflict free).
-template <int ENV, int MP, bool MOTOR, int N, int KC>
+// DBG: the verbose>=2 variant that also writes the per-step actions / observations / rewards (black_box_wrapper.py:208-213).
+template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
 __global__ void __launch_bounds__(kRolloutThreads)
 k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
           const int seg_steps) {
@@ -110,11 +111,54 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   if constexpr (ENV != FG_ENV_TOY) {
     cx0 = io.ctx[b * 4 + 0]; cx1 = io.ctx[b * 4 + 1]; cx2 = io.ctx[b * 4 + 2]; cx3 = io.ctx[b * 4 + 3];
   }
+  double ee180x = 0.0, ee180y = 0.0;     // rew_fct "unbounded": end effector latched at step 180 (hr_unbounded_reward.py:35-36)
   if constexpr (ENV == FG_ENV_HOLE_REACHER) {
     hole.xl = (float)(cx0 - cx1 / 2);    // hole_reacher.py:152 (x - width/2), rounded once to float32
     hole.xr = (float)(cx0 + cx1 / 2);
     hole.nd = (float)(-cx2);
+    if (c.rew_fct == 2 && steps > 0) {   // a later plan segment of the same episode: the latch lives in info[2..3]
+      ee180x = io.info[b * 4 + 2];
+      ee180y = io.info[b * 4 + 3];
+    }
   }
+
+  // full step observation (float64 trig, cast to float32 like _get_obs); returns its width
+  auto build_obs = [&](float* obs, double& ex, double& ey) -> int {
+    int no = 0;
+    if constexpr (ENV == FG_ENV_TOY) {
+      obs[no++] = -1.0f;
+      ex = ey = 0.0;
+    } else {
+      double th[N];
+      th[0] = q[0];
+#pragma unroll
+      for (int i = 1; i < N; ++i) th[i] = th[i - 1] + q[i];
+      end_effector64<N>(th, ex, ey);
+#pragma unroll
+      for (int i = 0; i < N; ++i) obs[i] = (float)cos(q[i]);
+#pragma unroll
+      for (int i = 0; i < N; ++i) obs[N + i] = (float)sin(q[i]);
+#pragma unroll
+      for (int i = 0; i < N; ++i) obs[2 * N + i] = (float)v[i];
+      no = 3 * N;
+      if constexpr (ENV == FG_ENV_HOLE_REACHER) {
+        obs[no++] = (float)cx1;
+        obs[no++] = (float)(ex - cx0);
+        obs[no++] = (float)(ey - (-cx2));
+      } else if constexpr (ENV == FG_ENV_VIAPOINT_REACHER) {
+        obs[no++] = (float)(ex - cx0);
+        obs[no++] = (float)(ey - cx1);
+        obs[no++] = (float)(ex - cx2);
+        obs[no++] = (float)(ey - cx3);
+      } else {
+        obs[no++] = (float)(ex - cx0);
+        obs[no++] = (float)(ey - cx1);
+      }
+      obs[no++] = (float)steps;
+    }
+    if (c.time_aware) obs[no++] = (float)((double)steps / (double)c.max_steps);
+    return no;
+  };
 
   // boundary condition of the plan (black_box_wrapper.py:110-114), float32 like the library
   float ybc[N], vbc[N];
@@ -319,20 +363,68 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
         if (!c.allow_self) selfc = self_collision<N>(q, th, cs, sn);
         if (!c.allow_wall) wallc = wall_collision<N>(s_m, cs, sn, hole, c.wall_mode);
         collided = selfc | wallc;
-        // hr_simple_reward.py:35-53
-        double dist_cost = 0.0, coll_cost = 0.0;
         success = false;
-        if (steps == 199 || collided) {
-          double ex, ey;
-          end_effector64<N>(th, ex, ey);
-          const double dx = ex - cx0, dy = ey - (-cx2);
-          const double dist = sqrt(dx * dx + dy * dy);
-          dist_cost = dist * dist;
-          coll_cost = collided ? 1.0 : 0.0;
-          success = (dist < 0.005) && !collided;
+        if (c.rew_fct == 0) {
+          // hr_simple_reward.py:35-53
+          double dist_cost = 0.0, coll_cost = 0.0;
+          if (steps == 199 || collided) {
+            double ex, ey;
+            end_effector64<N>(th, ex, ey);
+            const double dx = ex - cx0, dy = ey - (-cx2);
+            const double dist = sqrt(dx * dx + dy * dy);
+            dist_cost = dist * dist;
+            coll_cost = collided ? 1.0 : 0.0;
+            success = (dist < 0.005) && !collided;
+          }
+          reward = __dadd_rn(__dadd_rn(__dmul_rn(dist_cost, -1.0), __dmul_rn(acc_cost, -5e-8)),
+                             __dmul_rn(coll_cost, -c.penalty));
+        } else if (c.rew_fct == 1) {
+          // hr_dist_vel_acc_reward.py:20-60: distance / collision terms only on step 199 (a collision ends the episode, so
+          // the latched flag and collision_dist are this step's); factors (-1, -1e-4, -1e-6, -penalty, 0)
+          double dist_cost = 0.0, coll_cost = 0.0;
+          if (steps == 199) {
+            double ex, ey;
+            end_effector64<N>(th, ex, ey);
+            const double dx = ex - cx0, dy = ey - (-cx2);
+            const double dist = sqrt(dx * dx + dy * dy);
+            dist_cost = dist * dist;
+            coll_cost = collided ? dist * dist : 0.0;
+            success = (dist < 0.005) && !collided;
+          }
+          double vel_cost;
+          if constexpr (MOTOR) {
+            vel_cost = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) vel_cost += a64[i] * a64[i];
+          } else {      // float32 action: np.sum(v ** 2) is a float32 sum
+            float s32 = 0.f;
+#pragma unroll
+            for (int i = 0; i < N; ++i) s32 = __fadd_rn(s32, __fmul_rn(a32[i], a32[i]));
+            vel_cost = (double)s32;
+          }
+          reward = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dist_cost, -1.0), __dmul_rn(vel_cost, -1e-4)),
+                                       __dmul_rn(acc_cost, -1e-6)), __dmul_rn(coll_cost, -c.penalty));
+        } else {
+          // hr_unbounded_reward.py:17-60: end effector latched at step 180 (or on collision); factors (1, -5e-6)
+          double dist_reward = 0.0;
+          if (steps == 180 || steps == 199 || collided) {
+            double ex, ey;
+            end_effector64<N>(th, ex, ey);
+            if (steps == 180 || collided) {
+              ee180x = ex;
+              ee180y = ey;
+            }
+            if (steps == 199 || collided) {
+              const double dx = ee180x - cx0, dy = ee180y - (-cx2);
+              const double dist = sqrt(dx * dx + dy * dy);
+              if (collided) dist_reward = 0.25 * exp(-dist);
+              else if (ey > 0) dist_reward = exp(-dist);
+              else dist_reward = 1 - ee180y;
+              success = !collided;
+            }
+          }
+          reward = __dadd_rn(dist_reward, __dmul_rn(acc_cost, -5e-6));
         }
-        reward = __dadd_rn(__dadd_rn(__dmul_rn(dist_cost, -1.0), __dmul_rn(acc_cost, -5e-8)),
-                           __dmul_rn(coll_cost, -c.penalty));
         terminated = collided;
       } else if constexpr (ENV == FG_ENV_VIAPOINT_REACHER) {
         // viapoint_reacher.py:79-107 (App. A.6-Q1/Q2: -inf start, `acc` is the action)
@@ -402,10 +494,18 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     truncated = steps >= c.max_steps;       // gymnasium TimeLimit (App. A.6-Q12)
     ret += reward;
 
-    if (io.dbg_rewards) io.dbg_rewards[b * T + t] = reward;
-    if (io.dbg_actions) {
+    if constexpr (DBG) {
+      if (io.dbg_rewards) io.dbg_rewards[b * T + t] = reward;
+      if (io.dbg_actions) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) io.dbg_actions[(b * T + t) * N + i] = a64[i];
+        for (int i = 0; i < N; ++i) io.dbg_actions[(b * T + t) * N + i] = a64[i];
+      }
+      if (io.dbg_obs) {
+        float so[FG_MAX_OBS];
+        double ex, ey;
+        const int n_full = build_obs(so, ex, ey);
+        for (int j = 0; j < n_full; ++j) io.dbg_obs[(b * T + t) * n_full + j] = so[j];
+      }
     }
     if (terminated || truncated) {
       ++t;
@@ -437,50 +537,21 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   io.flags[b] = (terminated ? FG_FLAG_TERMINATED : 0u) | (truncated ? FG_FLAG_TRUNCATED : 0u) |
                 (success ? FG_FLAG_SUCCESS : 0u) | (collided ? FG_FLAG_COLLIDED : 0u);
 
-  // observation after the last executed step (float64 trig, cast to float32 like _get_obs)
+  // observation after the last executed step
   float obs[FG_MAX_OBS];
-  int no = 0;
-  if constexpr (ENV == FG_ENV_TOY) {
-    obs[no++] = -1.0f;
-  } else {
-    double th[N];
-    th[0] = q[0];
-#pragma unroll
-    for (int i = 1; i < N; ++i) th[i] = th[i - 1] + q[i];
+  {
     double ex, ey;
-    end_effector64<N>(th, ex, ey);
-#pragma unroll
-    for (int i = 0; i < N; ++i) obs[i] = (float)cos(q[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) obs[N + i] = (float)sin(q[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) obs[2 * N + i] = (float)v[i];
-    no = 3 * N;
-    if constexpr (ENV == FG_ENV_HOLE_REACHER) {
-      obs[no++] = (float)cx1;
-      obs[no++] = (float)(ex - cx0);
-      obs[no++] = (float)(ey - (-cx2));
+    build_obs(obs, ex, ey);
+    if constexpr (ENV == FG_ENV_HOLE_REACHER || ENV == FG_ENV_VIAPOINT_REACHER) {
       info0 = ex;
       info1 = ey;
-    } else if constexpr (ENV == FG_ENV_VIAPOINT_REACHER) {
-      obs[no++] = (float)(ex - cx0);
-      obs[no++] = (float)(ey - cx1);
-      obs[no++] = (float)(ex - cx2);
-      obs[no++] = (float)(ey - cx3);
-      info0 = ex;
-      info1 = ey;
-    } else {
-      obs[no++] = (float)(ex - cx0);
-      obs[no++] = (float)(ey - cx1);
     }
-    obs[no++] = (float)steps;
   }
-  if (c.time_aware) obs[no++] = (float)((double)steps / (double)c.max_steps);
   for (int j = 0; j < c.n_obs_out; ++j) io.obs[b * c.n_obs_out + j] = obs[c.obs_index[j]];
   io.info[b * 4 + 0] = info0;
   io.info[b * 4 + 1] = info1;
-  io.info[b * 4 + 2] = 0.0;
-  io.info[b * 4 + 3] = 0.0;
+  io.info[b * 4 + 2] = ee180x;
+  io.info[b * 4 + 3] = ee180y;
 #undef WSM
 }
 

@@ -5,8 +5,8 @@
 
 namespace fg {
 
-template <int ENV, int MP, bool MOTOR, int N, int KC>
-cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
+template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
+cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
                       int max_smem_optin, const char** why) {
   const int pw = N * weight_slots(MP, c.K);
   const size_t smem = sizeof(float) * rollout_smem_floats(c.T, c.cols_a, c.rows_b, c.cols_b, pw, kRolloutThreads);
@@ -14,7 +14,7 @@ cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int
     *why = "tables + per-thread weights exceed the shared memory of one SM (reduce n_steps or n_basis)";
     return cudaSuccess;
   }
-  auto kern = k_rollout<ENV, MP, MOTOR, N, KC>;
+  auto kern = k_rollout<ENV, MP, MOTOR, N, KC, DBG>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -22,6 +22,16 @@ cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int
   const long long blocks = (B + kRolloutThreads - 1) / kRolloutThreads;
   kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, io, B, seg_steps);
   return cudaGetLastError();
+}
+
+template <int ENV, int MP, bool MOTOR, int N, int KC>
+cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
+                      int max_smem_optin, const char** why) {
+  // the per-step debug outputs of verbose >= 2 are a separate instantiation: the hot variant carries none of their code.
+  // They always use run-time K (KC = 0) to keep the number of instantiations down.
+  if (io.dbg_actions || io.dbg_obs || io.dbg_rewards)
+    return launch_dbg<ENV, MP, MOTOR, N, 0, true>(c, io, B, seg_steps, stream, max_smem_optin, why);
+  return launch_dbg<ENV, MP, MOTOR, N, KC, false>(c, io, B, seg_steps, stream, max_smem_optin, why);
 }
 
 template <int ENV, int MP, bool MOTOR, int N>

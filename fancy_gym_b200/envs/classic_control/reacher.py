@@ -180,12 +180,11 @@ class HoleReacherEnv(BaseReacherEnv):
                  allow_wall_collision: bool = False, collision_penalty: float = 1000, rew_fct: str = "simple", **kwargs):
         if rew_fct not in ("simple", "vel_acc", "unbounded"):
             raise ValueError("Unknown reward function {}".format(rew_fct))      # hole_reacher.py:57-58
-        if rew_fct != "simple":
-            raise NotImplementedError(f"rew_fct={rew_fct!r}: only 'simple' (the registered -v0 default) is fused so far")
         self.initial_x, self.initial_width, self.initial_depth = hole_x, hole_width, hole_depth
         self.allow_wall_collision = allow_wall_collision
         self.collision_penalty = collision_penalty
         self.rew_fct = rew_fct
+        self.rew_fct_code = ("simple", "vel_acc", "unbounded").index(rew_fct)     # fg_config.rew_fct
         super().__init__(n_links, random_start, allow_self_collision, **kwargs)
 
     def _sample_numpy(self, rngs, seeds, random_start):

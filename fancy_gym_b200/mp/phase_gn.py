@@ -71,13 +71,15 @@ class PhaseGenerator:
     # -- numerics (float32 linear phase exactly as the library's elementwise torch ops) ---------
     def uniform(self) -> bool:
         """True when tau and delay are the same for every env of the batch (shared tables)."""
-        return self.tau.dim() == 0 and self.delay.dim() == 0
+        def same(x):
+            return x.dim() == 0 or x.numel() <= 1 or bool((x == x.reshape(-1)[0]).all())
+        return same(self.tau) and same(self.delay)
 
     def scalar_tau(self) -> float:
-        return float(self.tau)
+        return float(self.tau.reshape(-1)[0])
 
     def scalar_delay(self) -> float:
-        return float(self.delay)
+        return float(self.delay.reshape(-1)[0])
 
     def linear_phase32(self, times32: np.ndarray, clip_hi: bool = True) -> np.ndarray:
         tau, delay = np.float32(self.scalar_tau()), np.float32(self.scalar_delay())

@@ -98,7 +98,8 @@ typedef struct fg_config {
   int32_t allow_self_collision;
   int32_t allow_wall_collision;
   double collision_penalty;
-  int32_t rew_fct;             /* hole reacher: 0 = "simple" (hr_simple_reward.py) */
+  int32_t rew_fct;             /* hole reacher (hole_reacher.py:48-58): 0 = "simple" (hr_simple_reward.py),
+                                  1 = "vel_acc" (hr_dist_vel_acc_reward.py), 2 = "unbounded" (hr_unbounded_reward.py) */
   int32_t wall_mode;           /* 0 = exact interval search over the 100 samples/link (default),
                                   1 = literal evaluation of all 100 samples/link (hole_reacher.py:148-179) */
   int32_t time_aware;          /* append elapsed/max_episode_steps to obs (utils/wrappers.py:49-63) */
@@ -144,7 +145,8 @@ typedef struct fg_rollout_io {
   int32_t* length;         /* [B] executed steps = infos['trajectory_length'] */
   uint8_t* flags;          /* [B] FG_FLAG_* */
   float* obs;              /* [B, n_obs_out] observation after the last executed step */
-  double* info;            /* [B, 4] hole/viapoint: end_effector x,y; simple: reward_dist, reward_ctrl; [2..3] spare */
+  double* info;            /* [B, 4] hole/viapoint: end_effector x,y; simple: reward_dist, reward_ctrl;
+                              [2..3]: in/out state of rew_fct "unbounded" (end effector latched at step 180), else 0 */
   /* optional per-step outputs of verbose>=2 (black_box_wrapper.py:208-213); NULL to skip.
    * (infos['positions'] / ['velocities'] are the whole planned trajectory: use fg_trajgen.) */
   double* dbg_actions;     /* [B, T, dof] infos['step_actions'] */

@@ -17,32 +17,57 @@ import numpy as np
 from . import mp as omp
 from .reacher import BatchedReacher
 
-# ---- resolved configs of the three BASELINE envs (registry.py:62-129 merged with
-# ---- the per-env mp_wrapper.mp_config through nested_update, incl. the `_type` replace quirk) ----
-RESOLVED = {
-    "fancy_ProMP/HoleReacher-v0": dict(
-        env=dict(kind="hole", n_links=5, random_start=True, allow_self_collision=False,
-                 allow_wall_collision=False, hole_width=None, hole_depth=1, hole_x=None, collision_penalty=100),
-        traj=dict(trajectory_generator_type="promp", weights_scale=2),
-        phase=dict(phase_generator_type="linear"),
-        basis=dict(basis_generator_type="zero_rbf", num_basis=5, num_basis_zero_start=1, basis_bandwidth_factor=3.0),
-        ctrl=dict(controller_type="velocity"),
-    ),
-    "fancy_DMP/ViaPointReacher-v0": dict(
-        env=dict(kind="viapoint", n_links=5, allow_self_collision=False, collision_penalty=1000),
-        traj=dict(trajectory_generator_type="dmp", weights_scale=50),
-        phase=dict(phase_generator_type="exp", alpha_phase=2),
-        basis=dict(basis_generator_type="rbf", num_basis=5),
-        ctrl=dict(controller_type="velocity"),
-    ),
-    "fancy_ProDMP/SimpleReacher-v0": dict(
-        env=dict(kind="simple", n_links=2),
-        traj=dict(trajectory_generator_type="prodmp", duration=2.0, weights_scale=1.0),
-        phase=dict(phase_generator_type="exp", tau=1.5),
-        basis=dict(basis_generator_type="prodmp", alpha=10, num_basis=5),
-        ctrl=dict(controller_type="motor", p_gains=1.0, d_gains=0.1),
-    ),
+# ---- resolved configs of the twelve classic_control black-box ids: registry defaults (fancy_gym/envs/registry.py:62-129)
+# ---- merged with each env's mp_wrapper.mp_config through nested_update, incl. the `_type` replace quirk (:264-277) ----
+_MP_DEFAULTS = {
+    "ProMP": dict(traj=dict(trajectory_generator_type="promp"), phase=dict(phase_generator_type="linear"),
+                  basis=dict(basis_generator_type="zero_rbf", num_basis=5, num_basis_zero_start=1, basis_bandwidth_factor=3.0)),
+    "DMP": dict(traj=dict(trajectory_generator_type="dmp"), phase=dict(phase_generator_type="exp"),
+                basis=dict(basis_generator_type="rbf", num_basis=5)),
+    "ProDMP": dict(traj=dict(trajectory_generator_type="prodmp", duration=2.0, weights_scale=1.0),
+                   phase=dict(phase_generator_type="exp", tau=1.5),
+                   basis=dict(basis_generator_type="prodmp", alpha=10, num_basis=5)),
 }
+_DEFAULT_CTRL = dict(controller_type="motor", p_gains=1.0, d_gains=0.1)
+
+# envs/__init__.py:38-87 (registration kwargs) and */mp_wrapper.py (mp_config)
+_ENVS = {
+    "HoleReacher-v0": dict(
+        env=dict(kind="hole", n_links=5, random_start=True, allow_self_collision=False, allow_wall_collision=False,
+                 hole_width=None, hole_depth=1, hole_x=None, collision_penalty=100),
+        mp_config={"ProMP": dict(ctrl=dict(controller_type="velocity"), traj=dict(weights_scale=2)),
+                   "DMP": dict(ctrl=dict(controller_type="velocity"), traj=dict(weights_scale=500), phase=dict(alpha_phase=2.5)),
+                   "ProDMP": {}}),
+    "ViaPointReacher-v0": dict(
+        env=dict(kind="viapoint", n_links=5, allow_self_collision=False, collision_penalty=1000),
+        mp_config={"ProMP": dict(ctrl=dict(controller_type="velocity")),
+                   "DMP": dict(ctrl=dict(controller_type="velocity"), traj=dict(weights_scale=50), phase=dict(alpha_phase=2)),
+                   "ProDMP": {}}),
+    "SimpleReacher-v0": dict(
+        env=dict(kind="simple", n_links=2),
+        mp_config={"ProMP": dict(ctrl=dict(p_gains=0.6, d_gains=0.075)),
+                   "DMP": dict(ctrl=dict(p_gains=0.6, d_gains=0.075), traj=dict(weights_scale=50), phase=dict(alpha_phase=2)),
+                   "ProDMP": {}}),
+}
+_ENVS["LongSimpleReacher-v0"] = dict(env=dict(kind="simple", n_links=5), mp_config=_ENVS["SimpleReacher-v0"]["mp_config"])
+
+
+def _merge(base, update):
+    if any(k.endswith("_type") for k in update):
+        return dict(update)
+    out = dict(base)
+    out.update(update)
+    return out
+
+
+def _resolve(name, mp_type):
+    d, e = _MP_DEFAULTS[mp_type], _ENVS[name]
+    own = e["mp_config"][mp_type]
+    return dict(env=dict(e["env"]), traj=_merge(d["traj"], own.get("traj", {})), phase=_merge(d["phase"], own.get("phase", {})),
+                basis=_merge(d["basis"], own.get("basis", {})), ctrl=_merge(_DEFAULT_CTRL, own.get("ctrl", {})))
+
+
+RESOLVED = {f"fancy_{mp}/{name}": _resolve(name, mp) for name in _ENVS for mp in _MP_DEFAULTS}
 
 
 def controller_action(ctrl, des_pos, des_vel, c_pos, c_vel):
@@ -199,12 +224,12 @@ class BlackBoxOracle:
 
 
 def _snapshot(env):
-    return {k: copy.copy(getattr(env, k)) for k in ("q", "v", "acc", "steps", "J")}
+    return {k: copy.copy(getattr(env, k, None)) for k in ("q", "v", "acc", "steps", "J", "ee_latch")}
 
 
 def _restore(env, snap, mask):
     for k, old in snap.items():
-        cur = getattr(env, k)
+        cur = getattr(env, k, None)
         if old is None or cur is None:
             continue
         if cur.dtype != old.dtype:
@@ -213,7 +238,8 @@ def _restore(env, snap, mask):
 
 
 def make_oracle(env_id, mode="mirror", mp_overrides=None, **bb_kwargs):
-    """Builds the oracle for one of the three BASELINE env ids (RESOLVED above), mirroring
+    """Builds the oracle for one of the twelve classic_control ids (RESOLVED above; `mp_overrides` = {"env": {...},
+    "traj": ..., "phase": ..., "basis": ..., "ctrl": ...} updates the sections), mirroring
     make_bb (fancy_gym/utils/make_env_helpers.py:68-136): duration = max_episode_steps * dt,
     tau defaults to the duration, learn_sub_trajectories implies learn_tau, default bounds."""
     cfg = copy.deepcopy(RESOLVED[env_id])

@@ -245,8 +245,9 @@ class BatchedReacher:
         self.collision_penalty = collision_penalty
         self.initial_x, self.initial_depth, self.initial_width = hole_x, hole_depth, hole_width
         self.initial_via_target, self.initial_target = via_target, target
-        if kind == "hole" and rew_fct != "simple":
-            raise NotImplementedError("oracle restates rew_fct='simple' (the -v0 registration)")
+        if rew_fct not in ("simple", "vel_acc", "unbounded"):
+            raise ValueError("Unknown reward function {}".format(rew_fct))        # hole_reacher.py:57-58
+        self.rew_fct = rew_fct
         self.dt = DT
         self.compute_margins = True     # bench.py's CPU baseline switches the (non-reference) margin bookkeeping off
         self.double_collision_eval = False   # ... and evaluates the collision tests twice per step like the reference (App. A.6-Q3)
@@ -290,6 +291,7 @@ class BatchedReacher:
             self.hole_w = np.array([c["width"] for c in contexts], dtype=np.float64)
             self.hole_d = np.array([c["depth"] for c in contexts], dtype=np.float64)
             self.goal = np.stack([self.hole_x, -self.hole_d], axis=1)   # hole_reacher.py:100
+            self.ee_latch = np.zeros((B, 2))                            # hr_unbounded_reward.py:35-36 (end_eff_pos)
         else:
             self.goal = np.stack([c["goal"] for c in contexts]).astype(np.float64)
             if self.kind == "viapoint":
@@ -358,7 +360,8 @@ class BatchedReacher:
                 wall_collision(self.q, self.hole_x, self.hole_w, self.hole_d, self.allow_wall_collision, mg)
             collided = selfc | wallc
             margin = np.minimum(margin, wmargin)
-            reward, info = self._reward_hole(collided)
+            reward, info = {"simple": self._reward_hole, "vel_acc": self._reward_hole_vel_acc,
+                            "unbounded": self._reward_hole_unbounded}[self.rew_fct](collided)
         elif self.kind == "viapoint":
             collided = selfc
             reward, info = self._reward_viapoint(action, collided)
@@ -383,6 +386,41 @@ class BatchedReacher:
         factors = np.array((-1, -5e-8, -self.collision_penalty), dtype=np.float64)
         reward = dist_cost * factors[0] + acc_cost.astype(np.float64) * factors[1] + collision_cost * factors[2]
         return reward, dict(is_success=success, is_collided=collided.copy(), end_effector=ee.copy())
+
+    def _goal_dist_rowwise(self, ee):
+        """np.linalg.norm(ee - goal) per env, with the 1-D call the reference makes (BLAS nrm2 and the batched
+        sqrt(sum(x*x)) may differ in the last bit, which exp() would amplify)"""
+        return np.array([np.linalg.norm(ee[b] - self.goal[b]) for b in range(self.B)])
+
+    # hole_reacher/hr_dist_vel_acc_reward.py:20-60.  The reward object latches the first collision, but a collision
+    # also terminates the episode (hole_reacher.py:76-77), so inside an episode the latch equals this step's test and
+    # collision_dist is this step's distance.  Distance / collision terms exist on step 199 only.
+    def _reward_hole_vel_acc(self, collided):
+        ee = self.end_effector
+        last = self.steps == 199
+        dist = self._goal_dist_rowwise(ee)
+        dist_cost = np.where(last, dist ** 2, 0.0)
+        collision_cost = np.where(last, collided * dist ** 2, 0.0)
+        success = last & (dist < 0.005) & ~collided
+        vel_cost = np.sum(self.v ** 2, axis=1).astype(np.float64)
+        acc_cost = np.sum(self.acc ** 2, axis=1).astype(np.float64)
+        f = np.array((-1, -1e-4, -1e-6, -self.collision_penalty, 0), dtype=np.float64)
+        reward = dist_cost * f[0] + vel_cost * f[1] + acc_cost * f[2] + collision_cost * f[3]
+        return reward, dict(is_success=success, is_collided=collided.copy(), end_effector=ee.copy())
+
+    # hole_reacher/hr_unbounded_reward.py:17-60
+    def _reward_hole_unbounded(self, collided):
+        ee = self.end_effector
+        latch = (self.steps == 180) | collided
+        self.ee_latch = np.where(latch[:, None], ee, self.ee_latch)
+        last = (self.steps == 199) | collided
+        dist = self._goal_dist_rowwise(self.ee_latch)
+        dist_reward = np.where(collided, 0.25 * np.exp(-dist), np.where(ee[:, 1] > 0, np.exp(-dist), 1 - self.ee_latch[:, 1]))
+        dist_reward = np.where(last, dist_reward, 0.0)
+        success = last & ~collided
+        acc_cost = np.sum(self.acc ** 2, axis=1).astype(np.float64)
+        reward = dist_reward * 1.0 + acc_cost * -5e-6
+        return reward, dict(is_success=success, is_collided=collided.copy(), end_effector=ee.copy(), joints=self.q.copy())
 
     # viapoint_reacher/viapoint_reacher.py:79-107  (App. A.6-Q1: starts from -inf; Q2: `acc` is the action)
     def _reward_viapoint(self, action, collided):

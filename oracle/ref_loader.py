@@ -97,7 +97,7 @@ REF_ENV_KWARGS = {
 }
 
 
-def make_step_env(ns, name):
+def make_step_env(ns, name, **overrides):
     cls = {"HoleReacher-v0": ns.HoleReacherEnv, "ViaPointReacher-v0": ns.ViaPointReacherEnv,
            "SimpleReacher-v0": ns.SimpleReacherEnv, "LongSimpleReacher-v0": ns.SimpleReacherEnv}[name]
-    return cls(**REF_ENV_KWARGS[name])
+    return cls(**{**REF_ENV_KWARGS[name], **overrides})

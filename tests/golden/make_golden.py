@@ -31,13 +31,28 @@ from oracle import ref_loader as rl  # noqa: E402
 from oracle.blackbox import RESOLVED, make_oracle  # noqa: E402
 from oracle.reacher import BatchedReacher  # noqa: E402
 
+_HOLE = dict(n_links=5, random_start=True, hole_width=None, hole_depth=1, hole_x=None, collision_penalty=100)
 ENV_CASES = [
-    # name, oracle kind, oracle kwargs, seeds, amplitudes
-    ("HoleReacher-v0", "hole", dict(n_links=5, random_start=True, hole_width=None, hole_depth=1, hole_x=None,
-                                    collision_penalty=100), [0, 1, 2, 3, 4, 5, 6, 7], [0.3, 1.5, 6.0, 3.0, 0.1, 2.0, 4.0, 1.0]),
-    ("ViaPointReacher-v0", "viapoint", dict(n_links=5, collision_penalty=1000), [0, 1, 2, 3], [0.3, 6.0, 1.5, 3.0]),
-    ("SimpleReacher-v0", "simple", dict(n_links=2), [0, 1, 2, 3], [5.0, 20.0, 100.0, 1.0]),
-    ("LongSimpleReacher-v0", "simple", dict(n_links=5), [0, 1], [5.0, 50.0]),
+    # key, reference env name, oracle kind, oracle kwargs, seeds, amplitudes, constructor overrides given to BOTH sides
+    ("HoleReacher-v0", "HoleReacher-v0", "hole", _HOLE, [0, 1, 2, 3, 4, 5, 6, 7], [0.3, 1.5, 6.0, 3.0, 0.1, 2.0, 4.0, 1.0], {}),
+    ("ViaPointReacher-v0", "ViaPointReacher-v0", "viapoint", dict(n_links=5, collision_penalty=1000), [0, 1, 2, 3],
+     [0.3, 6.0, 1.5, 3.0], {}),
+    ("SimpleReacher-v0", "SimpleReacher-v0", "simple", dict(n_links=2), [0, 1, 2, 3], [5.0, 20.0, 100.0, 1.0], {}),
+    ("LongSimpleReacher-v0", "LongSimpleReacher-v0", "simple", dict(n_links=5), [0, 1], [5.0, 50.0], {}),
+    # the other two HoleReacher reward functions (hole_reacher.py:48-58)
+    ("HoleReacher-v0+vel_acc", "HoleReacher-v0", "hole", _HOLE, [0, 1, 2, 3, 4, 5], [0.3, 1.5, 6.0, 0.1, 2.0, 1.0], dict(rew_fct="vel_acc")),
+    ("HoleReacher-v0+unbounded", "HoleReacher-v0", "hole", _HOLE, [0, 1, 2, 3, 4, 5], [0.3, 1.5, 6.0, 0.1, 2.0, 1.0], dict(rew_fct="unbounded")),
+    # constructor options: collisions allowed, fixed hole, fixed start
+    ("HoleReacher-v0+free", "HoleReacher-v0", "hole", _HOLE, [0, 1, 2, 3], [6.0, 3.0, 4.0, 2.0],
+     dict(allow_self_collision=True, allow_wall_collision=True)),
+    ("HoleReacher-v0+fixed", "HoleReacher-v0", "hole", _HOLE, [0, 1, 2], [0.3, 1.5, 3.0],
+     dict(hole_x=1.5, hole_width=0.3, hole_depth=0.8, random_start=False)),
+    ("ViaPointReacher-v0+fixed", "ViaPointReacher-v0", "viapoint", dict(n_links=5, collision_penalty=1000), [0, 1], [0.3, 6.0],
+     dict(via_target=(1.0, 1.0), target=(3.0, 2.0), random_start=True)),
+    ("ViaPointReacher-v0+free", "ViaPointReacher-v0", "viapoint", dict(n_links=5, collision_penalty=1000), [0, 1], [6.0, 3.0],
+     dict(allow_self_collision=True)),
+    ("SimpleReacher-v0+fixed", "SimpleReacher-v0", "simple", dict(n_links=2), [0, 1], [5.0, 20.0],
+     dict(target=(0.5, 1.0), random_start=False)),
 ]
 
 
@@ -51,14 +66,15 @@ def close64(a, b):
 
 def gen_env_kat(ns):
     out = {}
-    for name, kind, kw, seeds, amps in ENV_CASES:
+    for key, name, kind, kw, seeds, amps, over in ENV_CASES:
+        kw = {**kw, **over}
         n = kw["n_links"]
         T = 200
         obs_dim = None
         rec = dict(obs0=[], obs=[], rew=[], term=[], length=[])
         ctx_rec = []
         for s, A in zip(seeds, amps):
-            env = rl.make_step_env(ns, name)
+            env = rl.make_step_env(ns, name, **over)
             ob0, _ = env.reset(seed=s)
             obs_dim = ob0.shape[0]
             obs = np.zeros((T, obs_dim), np.float32)
@@ -80,7 +96,8 @@ def gen_env_kat(ns):
                 ctx_rec.append([*env._via_point, *env._goal, env._start_pos[0]])
             else:
                 ctx_rec.append([*env._goal, env._start_pos[0]])
-        key = name.replace("-", "_")
+        name = key
+        key = key.replace("-", "_")
         out[f"{key}/seeds"] = np.array(seeds)
         out[f"{key}/amps"] = np.array(amps)
         out[f"{key}/ctx"] = np.array(ctx_rec, dtype=np.float64)
@@ -135,49 +152,74 @@ class TorchTrajGen:
         self.tg.reset()
 
 
-def build_reference_bb(ns, env_id, mode, bb_kwargs):
+def build_reference_bb(ns, env_id, mode, bb_kwargs, env_over=None):
     """reference BlackBoxWrapper(MPWrapper([TimeAwareObservation](TimeLimit(env)))) as make_bb
     (utils/make_env_helpers.py:68-136) would assemble it, with the oracle MP as traj_gen."""
     cfg = RESOLVED[env_id]
     name = env_id.split("/")[1]
-    env = ns.TimeLimit(rl.make_step_env(ns, name), 200)
+    env = ns.TimeLimit(rl.make_step_env(ns, name, **(env_over or {})), 200)
     if bb_kwargs.get("replanning_schedule") or bb_kwargs.get("learn_sub_trajectories"):
         taw = importlib.import_module("fancy_gym.utils.wrappers").TimeAwareObservation
         env = taw(env)
     wrap = {"HoleReacher-v0": ns.MPWrapper_HoleReacher, "ViaPointReacher-v0": ns.MPWrapper_ViaPoint,
-            "SimpleReacher-v0": ns.MPWrapper_SimpleReacher}[name]
+            "SimpleReacher-v0": ns.MPWrapper_SimpleReacher, "LongSimpleReacher-v0": ns.MPWrapper_SimpleReacher}[name]
     env = wrap(env)
-    orc = make_oracle(env_id, mode=mode, **bb_kwargs)       # only to get an identically configured traj_gen
+    orc = make_oracle(env_id, mode=mode, mp_overrides={"env": env_over or {}}, **bb_kwargs)   # only for an identically configured traj_gen
     ctrl = ns.get_controller(**cfg["ctrl"])
     return ns.BlackBoxWrapper(env, TorchTrajGen(orc.traj_gen), ctrl, duration=2.0, verbose=2, **bb_kwargs)
 
 
+def n_params_of(env_id):
+    cfg = RESOLVED[env_id]
+    per_dof = cfg["basis"]["num_basis"] + (0 if cfg["traj"]["trajectory_generator_type"] == "promp" else 1)
+    return cfg["env"]["n_links"] * per_dof
+
+
 def params_for(env_id, seed, n_plans):
-    P = {"fancy_ProMP/HoleReacher-v0": 25, "fancy_DMP/ViaPointReacher-v0": 30, "fancy_ProDMP/SimpleReacher-v0": 12}[env_id]
     rng = np.random.default_rng(1234 + seed)
-    return (0.5 * rng.standard_normal((n_plans, P))).astype(np.float32)
+    return (0.5 * rng.standard_normal((n_plans, n_params_of(env_id)))).astype(np.float32)
 
 
+_REPLAN25 = dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4)
+# file name, env id, seeds, black-box kwargs[, env constructor overrides]
 BB_CASES = [
     ("bb_holereacher_promp", "fancy_ProMP/HoleReacher-v0", list(range(32)), {}),
     ("bb_viapoint_dmp", "fancy_DMP/ViaPointReacher-v0", list(range(8)), {}),
     ("bb_simplereacher_prodmp", "fancy_ProDMP/SimpleReacher-v0", list(range(8)), {}),
-    ("bb_simplereacher_prodmp_replan", "fancy_ProDMP/SimpleReacher-v0", list(range(8)),
-     dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4, condition_on_desired=False)),
-    ("bb_simplereacher_prodmp_replan_cod", "fancy_ProDMP/SimpleReacher-v0", list(range(8)),
-     dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4, condition_on_desired=True)),
+    ("bb_simplereacher_prodmp_replan", "fancy_ProDMP/SimpleReacher-v0", list(range(8)), dict(_REPLAN25, condition_on_desired=False)),
+    ("bb_simplereacher_prodmp_replan_cod", "fancy_ProDMP/SimpleReacher-v0", list(range(8)), dict(_REPLAN25, condition_on_desired=True)),
     ("bb_holereacher_promp_replan", "fancy_ProMP/HoleReacher-v0", list(range(8)),
      dict(replanning_schedule=lambda p, v, o, a, t: t % 50 == 0)),
+    # the rest of the classic_control x MP matrix registered at envs/__init__.py:38-87
+    ("bb_holereacher_dmp", "fancy_DMP/HoleReacher-v0", list(range(6)), {}),
+    ("bb_holereacher_prodmp", "fancy_ProDMP/HoleReacher-v0", list(range(6)), {}),
+    ("bb_viapoint_promp", "fancy_ProMP/ViaPointReacher-v0", list(range(6)), {}),
+    ("bb_viapoint_prodmp", "fancy_ProDMP/ViaPointReacher-v0", list(range(6)), {}),
+    ("bb_simplereacher_promp", "fancy_ProMP/SimpleReacher-v0", list(range(6)), {}),
+    ("bb_simplereacher_dmp", "fancy_DMP/SimpleReacher-v0", list(range(6)), {}),
+    ("bb_longsimplereacher_promp", "fancy_ProMP/LongSimpleReacher-v0", list(range(4)), {}),
+    ("bb_longsimplereacher_dmp", "fancy_DMP/LongSimpleReacher-v0", list(range(4)), {}),
+    ("bb_longsimplereacher_prodmp", "fancy_ProDMP/LongSimpleReacher-v0", list(range(4)), {}),
+    # HoleReacher reward functions through the black-box loop (the "unbounded" latch has to survive re-planning)
+    ("bb_holereacher_promp_vel_acc", "fancy_ProMP/HoleReacher-v0", list(range(8)), {}, dict(rew_fct="vel_acc")),
+    ("bb_holereacher_promp_unbounded", "fancy_ProMP/HoleReacher-v0", list(range(8)), {}, dict(rew_fct="unbounded")),
+    ("bb_holereacher_prodmp_unbounded_replan", "fancy_ProDMP/HoleReacher-v0", list(range(6)),
+     dict(replanning_schedule=lambda p, v, o, a, t: t % 60 == 0, condition_on_desired=True), dict(rew_fct="unbounded")),
 ]
 
 
+def bb_case(case):
+    """(file name, env id, seeds, black-box kwargs, env overrides)"""
+    return (*case, {}) if len(case) == 4 else case
+
+
 def gen_bb(ns):
-    for fname, env_id, seeds, bbk in BB_CASES:
+    for fname, env_id, seeds, bbk, env_over in map(bb_case, BB_CASES):
         n_plans = 8 if bbk.get("replanning_schedule") else 1
         rec = {k: [] for k in ("obs0", "params", "positions", "velocities", "step_obs", "step_rewards",
                                "ret", "length", "terminated", "truncated", "obs", "n_calls")}
         for s in seeds:
-            bb = build_reference_bb(ns, env_id, "shipped", bbk)
+            bb = build_reference_bb(ns, env_id, "shipped", bbk, env_over)
             ob0, _ = bb.reset(seed=s)
             th = params_for(env_id, s, n_plans)
             per = {k: [] for k in rec if k not in ("obs0", "params", "n_calls")}
@@ -209,7 +251,7 @@ def gen_bb(ns):
         np.savez_compressed(os.path.join(HERE, fname + ".npz"), **out)
 
         # ---- pin the oracle's loop (same 'shipped' MP) against the reference's BlackBoxWrapper ----
-        orc = make_oracle(env_id, mode="shipped", verbose=2, **bbk)
+        orc = make_oracle(env_id, mode="shipped", verbose=2, mp_overrides={"env": env_over}, **bbk)
         ob0 = orc.reset(seeds=seeds)
         assert np.array_equal(ob0, out["obs0"]), fname
         alive = np.ones(len(seeds), bool)

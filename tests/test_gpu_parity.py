@@ -15,7 +15,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle.blackbox import make_oracle  # noqa: E402
-from tests.golden.make_golden import BB_CASES  # noqa: E402
+from tests.golden.make_golden import BB_CASES, bb_case, n_params_of  # noqa: E402
 
 TIE_EPS = 1e-5
 
@@ -78,11 +78,11 @@ def test_trajgen_empty_and_single():
 @pytest.mark.parametrize("case", BB_CASES, ids=[c[0] for c in BB_CASES])
 def test_rollout_matches_reference_goldens(case, golden_dir):
     fancy_gym = _fg()
-    fname, env_id, seeds, bbk = case
+    fname, env_id, seeds, bbk, env_over = bb_case(case)
     g = np.load(os.path.join(golden_dir, fname + ".npz"))
-    override = {"black_box_kwargs": dict(bbk)} if bbk else {}
+    override = {"black_box_kwargs": dict(bbk, verbose=2)}
     B = len(seeds)
-    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override=override)
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override=override, **env_over)
     obs0, _ = env.reset(seed=np.array(seeds), options={"as_numpy": True})
     assert np.allclose(obs0, g["obs0"], rtol=0, atol=1e-6)
     n_plans = g["params"].shape[1]
@@ -103,25 +103,52 @@ def test_rollout_matches_reference_goldens(case, golden_dir):
             # reference's own finite-difference noise ~ 2^-23 |pos| / dt ~ 3e-5
             oscale = np.maximum(1.0, np.abs(g["obs"][b, i]))
             assert (np.abs(obs[b] - g["obs"][b, i]) <= 5e-5 * oscale).all(), (fname, b, i, obs[b], g["obs"][b, i])
+            # verbose=2 infos: the planned trajectory and the per-step observations / rewards of the reference's loop
+            L = g["length"][b, i]
+            assert rel_err(info["positions"][b], g["positions"][b, i]).max() < 1e-5
+            vscale = max(1.0, np.abs(g["velocities"][b, i]).max())
+            assert rel_err(info["velocities"][b], g["velocities"][b, i], scale=vscale).max() < 3e-5
+            so, so_ref = info["step_observations"][b, :L], g["step_obs"][b, i, :L]
+            tol = np.full(so.shape[1], 5e-5)
+            n = env.unwrapped.n_links
+            tol[2 * n:3 * n] = 3e-4        # joint velocities: float32 finite differences of the trajectory (see above)
+            assert (np.abs(so - so_ref) <= tol * np.maximum(1.0, np.abs(so_ref))).all(), \
+                (fname, b, i, np.abs(so - so_ref).max(axis=0))
+            sr, sr_ref = info["step_rewards"][b, :L], g["step_rewards"][b, i, :L]
+            fin = np.isfinite(sr_ref)
+            assert np.array_equal(sr[~fin], sr_ref[~fin])
+            # per-step rewards are dominated by 5e-8 * sum(acc^2) with acc = dv/dt of float32 finite differences
+            assert (np.abs(sr[fin] - sr_ref[fin]) <= 1e-5 * np.maximum(1.0, np.abs(sr_ref[fin])) + 1e-4 * np.abs(sr_ref[fin])).all(), (fname, b, i)
 
 
 # --------------------------------------------------------------------------------------------
 # fused rollout against the oracle on seeded random inputs (thousands of envs)
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env_id,sigma", [("fancy_ProMP/HoleReacher-v0", 0.25), ("fancy_ProMP/HoleReacher-v0", 1.0),
-                                          ("fancy_DMP/ViaPointReacher-v0", 1.0), ("fancy_ProDMP/SimpleReacher-v0", 1.0)])
-def test_rollout_matches_oracle_random(env_id, sigma):
+ALL_IDS = [f"fancy_{mp}/{name}" for name in ("HoleReacher-v0", "ViaPointReacher-v0", "SimpleReacher-v0", "LongSimpleReacher-v0")
+           for mp in ("ProMP", "DMP", "ProDMP")]
+RANDOM_CASES = [("fancy_ProMP/HoleReacher-v0", 0.25, {}), ("fancy_ProMP/HoleReacher-v0", 1.0, {}),
+                ("fancy_DMP/ViaPointReacher-v0", 1.0, {}), ("fancy_ProDMP/SimpleReacher-v0", 1.0, {})]
+RANDOM_CASES += [(i, 0.5, {}) for i in ALL_IDS if i not in [c[0] for c in RANDOM_CASES]]
+RANDOM_CASES += [("fancy_ProMP/HoleReacher-v0", 0.5, dict(rew_fct="vel_acc")), ("fancy_ProMP/HoleReacher-v0", 0.5, dict(rew_fct="unbounded")),
+                 ("fancy_ProMP/HoleReacher-v0", 1.0, dict(allow_self_collision=True)),
+                 ("fancy_ProMP/HoleReacher-v0", 1.0, dict(allow_wall_collision=True, hole_x=1.0, hole_width=0.4, hole_depth=0.7)),
+                 ("fancy_DMP/ViaPointReacher-v0", 1.0, dict(allow_self_collision=True, random_start=True))]
+
+
+@pytest.mark.parametrize("env_id,sigma,env_over", RANDOM_CASES,
+                         ids=[f"{c[0]}-{c[1]}" + "".join(f"-{k}={v}" for k, v in c[2].items()) for c in RANDOM_CASES])
+def test_rollout_matches_oracle_random(env_id, sigma, env_over):
     fancy_gym = _fg()
-    B = 2048 + 37
-    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0")
+    B = 2048 + 37 if not env_over and env_id in P_OF else 512 + 5
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", **env_over)
     env.reset(seed=100)
     rng = np.random.default_rng(11)
-    params = (sigma * rng.standard_normal((B, P_OF[env_id]))).astype(np.float32)
+    params = (sigma * rng.standard_normal((B, n_params_of(env_id)))).astype(np.float32)
     obs, ret, te, tr, info = env.step(torch.as_tensor(params, device="cuda:0"))
     obs, ret, te, tr = obs.cpu().numpy(), ret.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
     length = info["trajectory_length"].cpu().numpy()
 
-    orc = make_oracle(env_id, mode="mirror")
+    orc = make_oracle(env_id, mode="mirror", mp_overrides={"env": env_over})
     orc.reset(seeds=100 + np.arange(B))
     o_obs, o_ret, o_te, o_tr, o_info = orc.step(params)
     tie = o_info["min_margin"] < TIE_EPS
@@ -137,6 +164,8 @@ def test_rollout_matches_oracle_random(env_id, sigma):
     for k in ("is_success", "is_collided"):
         if k in info:
             assert np.array_equal(info[k].cpu().numpy()[m], o_info[k][m])
+    if "joints" in o_info:
+        assert rel_err(info["joints"].cpu().numpy()[m], o_info["joints"][m], scale=np.pi).max() < 1e-5
     if "end_effector" in info:
         assert rel_err(info["end_effector"].cpu().numpy()[m], o_info["end_effector"][m], scale=5.0).max() < 1e-5
     if "reward_dist" in info:

@@ -9,14 +9,15 @@ from oracle.blackbox import make_oracle
 from oracle.reacher import (BatchedReacher, sample_hole_context, sample_simple_context,
                             sample_viapoint_context)
 
-from tests.golden.make_golden import BB_CASES, ENV_CASES, close64
+from tests.golden.make_golden import BB_CASES, ENV_CASES, bb_case, close64
 
 
 @pytest.mark.parametrize("case", ENV_CASES, ids=[c[0] for c in ENV_CASES])
 def test_env_restatement_matches_reference_files(case, golden_dir):
-    name, kind, kw, seeds, amps = case
+    key, name, kind, kw, seeds, amps, over = case
+    kw = {**kw, **over}
     g = np.load(os.path.join(golden_dir, "env_kat.npz"))
-    key = name.replace("-", "_")
+    key = key.replace("-", "_")
     n = kw["n_links"]
     o = BatchedReacher(kind, **kw)
     ob0 = o.reset(seeds=seeds)
@@ -73,9 +74,9 @@ def test_survey_rollout_kats():
 
 @pytest.mark.parametrize("case", BB_CASES, ids=[c[0] for c in BB_CASES])
 def test_blackbox_loop_matches_reference_wrapper(case, golden_dir):
-    fname, env_id, seeds, bbk = case
+    fname, env_id, seeds, bbk, env_over = bb_case(case)
     g = np.load(os.path.join(golden_dir, fname + ".npz"))
-    orc = make_oracle(env_id, mode="shipped", verbose=2, **bbk)
+    orc = make_oracle(env_id, mode="shipped", verbose=2, mp_overrides={"env": env_over}, **bbk)
     ob0 = orc.reset(seeds=seeds)
     assert np.array_equal(ob0, g["obs0"])
     n_plans = g["params"].shape[1]
