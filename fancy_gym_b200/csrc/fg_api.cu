@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "fancy_gym_b200.h"
 #include "fg_device.cuh"
@@ -34,6 +35,7 @@ struct fg_handle {
   int device;
   float* d_tab_a;
   float* d_tab_b;
+  float* d_quad_rec;
   int max_smem_optin;
   int sm_count;
 };
@@ -62,7 +64,7 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
   if (!h) return fail(FG_ERR_NOMEM, "out of host memory");
   h->cfg = *cfg;
   h->device = device;
-  h->d_tab_a = h->d_tab_b = nullptr;
+  h->d_tab_a = h->d_tab_b = h->d_quad_rec = nullptr;
   int prev = 0;
   FG_CUDA(cudaGetDevice(&prev));
   FG_CUDA(cudaSetDevice(device));
@@ -110,6 +112,34 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
     FG_CUDA(cudaMemcpy(h->d_tab_b, cfg->tab_b, nb * sizeof(float), cudaMemcpyHostToDevice));
   }
   d.tab_a = h->d_tab_a; d.tab_b = h->d_tab_b;
+  if (cfg->mp_kind == FG_MP_PROMP || cfg->mp_kind == FG_MP_PRODMP) {
+    // quad records for fg_trajgen (layout: fg_device.cuh); 1/dt is the correctly rounded float32 reciprocal, like __frcp_rn
+    const int kw = d.cols_a, r4 = fg::traj_r4(kw), rec4 = fg::traj_rec4(cfg->mp_kind, kw), nq = (T + 3) / 4;
+    const int rowf = r4 * 4, recf = rec4 * 4;
+    std::vector<float> rec((size_t)nq * recf, 0.f);
+    for (int q = 0; q < nq; ++q) {
+      float* o = rec.data() + (size_t)q * recf;
+      const int rows = (cfg->mp_kind == FG_MP_PROMP) ? 5 : 4;
+      for (int r = 0; r < rows; ++r) {
+        const int t = (4 * q + r < T - 1) ? 4 * q + r : T - 1;
+        for (int col = 0; col < kw; ++col) {
+          o[r * rowf + col] = cfg->tab_a[(size_t)t * kw + col];
+          if (cfg->mp_kind == FG_MP_PRODMP) o[(4 + r) * rowf + col] = cfg->tab_b[(size_t)t * kw + col];
+        }
+      }
+      if (cfg->mp_kind == FG_MP_PROMP) {
+        for (int j = 0; j < 4; ++j) {
+          const int tb = (4 * q + j < d.rows_b - 1) ? 4 * q + j : d.rows_b - 1;
+          o[5 * rowf + j] = cfg->tab_b[tb];
+          o[5 * rowf + 4 + j] = 1.0f / cfg->tab_b[tb];
+        }
+      }
+    }
+    FG_CUDA(cudaMalloc(&h->d_quad_rec, rec.size() * sizeof(float)));
+    FG_CUDA(cudaMemcpy(h->d_quad_rec, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice));
+    d.quad_rec = reinterpret_cast<const float4*>(h->d_quad_rec);
+    d.quad_rec4 = rec4;
+  }
   h->cfg.tab_a = h->cfg.tab_b = nullptr;   // host pointers are not retained
   FG_CUDA(cudaSetDevice(prev));
   *out = h;
@@ -120,6 +150,7 @@ fg_status fg_destroy(fg_handle* h) {
   if (!h) return FG_OK;
   if (h->d_tab_a) cudaFree(h->d_tab_a);
   if (h->d_tab_b) cudaFree(h->d_tab_b);
+  if (h->d_quad_rec) cudaFree(h->d_quad_rec);
   delete h;
   return FG_OK;
 }

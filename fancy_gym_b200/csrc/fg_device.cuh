@@ -35,7 +35,19 @@ struct DevCfg {
   const float* tab_a;   // device
   const float* tab_b;   // device
   int cols_a, rows_b, cols_b;
+  const float4* quad_rec;   // device: the tables re-packed per quad of time points for fg_trajgen (fg_trajgen.cuh), or null
+  int quad_rec4;            // float4 per record
 };
+
+// ---- quad records of the closed-form trajectory kernel (packed on the host in fg_create) -------------------------
+//   ProMP : 5 table rows (t0 .. t0+4; the 5th feeds the finite difference of row t0+3), 4 time increments, 4 reciprocals
+//   ProDMP: 4 position rows, 4 velocity rows
+// padded to an ODD number of float4 so that the lanes of a quarter warp, which read consecutive records, hit distinct
+// shared-memory bank groups.
+__host__ __device__ constexpr int traj_r4(int kw) { return (kw + 3) / 4; }
+__host__ __device__ constexpr int traj_rec4(int mp, int kw) {
+  return ((mp == FG_MP_PROMP) ? 5 * traj_r4(kw) + 2 : 8 * traj_r4(kw)) | 1;
+}
 
 // ------------------------------------------------------------------------------------------
 // trigonometry: argument reduction in float64 (keeps *relative* accuracy of sin near multiples

@@ -1,4 +1,6 @@
 // Kernel selection for the two entry points; trajectory-generation instantiations live here.
+#include <cstdlib>
+
 #include "fg_dispatch.h"
 #include "fg_trajgen.cuh"
 
@@ -21,9 +23,8 @@ template <int MP, int N, int KW>
 cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel, float* pos_out,
                           float* vel_out, long long B, cudaStream_t stream, int max_smem_optin, int sm_count,
                           const char** why) {
-  auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
-  const int RA = traj_row_stride(c.cols_a), RB = (MP == FG_MP_PROMP) ? 1 : RA;
-  const size_t fl = (size_t)kTrajWarps * 2 * kTrajStageFloats + (size_t)c.T * RA + pad4(c.rows_b * RB) + pad4(c.rows_b) +
+  const int nq = (c.T + 3) / 4;
+  const size_t fl = (size_t)kTrajWarps * 2 * kTrajStageFloats + (size_t)nq * traj_rec4(MP, c.cols_a) * 4 +
                     (KW == 0 ? (size_t)kTrajWarps * N * c.cols_a : 0);
   const size_t smem = fl * sizeof(float);
   if (smem > (size_t)max_smem_optin) {
@@ -35,14 +36,14 @@ cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  // persistent grid: (resident blocks per SM) x (SM count), each warp strides over envs
-  int per_sm = 1;
-  cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTrajThreads, smem);
-  if (eo != cudaSuccess) return eo;
-  long long want = (B + kTrajWarps - 1) / kTrajWarps;
-  long long cap = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
-  const unsigned blocks = (unsigned)(want < cap ? want : cap);
-  kern<<<blocks, kTrajThreads, smem, stream>>>(c, params, bc_pos, bc_vel, pos_out, vel_out, B);
+  // blocks of `epb` consecutive envs, dynamically scheduled (see the kernel): large enough to amortise the per-block
+  // table staging, small enough for >= ~8 blocks per SM
+  int epb = 64;
+  while (epb > kTrajWarps && (B + epb - 1) / epb < (long long)sm_count * 8) epb >>= 1;
+  const char* env_epb = getenv("FG_TRAJ_EPB");
+  if (env_epb && atoi(env_epb) > 0) epb = atoi(env_epb);
+  const unsigned blocks = (unsigned)((B + epb - 1) / epb);
+  kern<<<blocks, kTrajThreads, smem, stream>>>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, epb);
   return cudaGetLastError();
 }
 

@@ -24,61 +24,57 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 constexpr int kTrajStageFloats = 1024;   // per warp and per output array: a whole [T, dof] trajectory when T*dof <= 1024
 
-__host__ __device__ constexpr int traj_row_stride(int kw) {   // float4-padded, and an ODD number of float4 per row so
-  int r = (kw + 3) & ~3;                                      // that 8 lanes reading 8 different rows hit 8 bank groups
-  return ((r / 4) & 1) ? r : r + 4;
-}
-
 // closed-form MPs: ProMP (KW = K weighted columns) and ProDMP (KW = K+3: [y_b, tau*dy_b, w.., g]).
-// KW > 0: compile-time column count, weights in registers, float4 row loads; KW == 0: run-time fallback.
-// One warp owns one env: lanes own consecutive time points (31 per pass for ProMP, whose lane 31 only supplies
-// pos[t+1] for lane 30's finite difference through a warp shuffle; 32 for ProDMP).  The env's whole pos / vel
-// block is staged in shared memory and leaves the SM as two TMA bulk stores (cp.async.bulk shared->global) issued
-// by one lane, i.e. full 128-byte lines and no per-element store instructions.
+// KW > 0: compile-time column count, weights in registers; KW == 0: run-time fallback with the weights in shared memory.
+//
+// One warp owns one env; a lane owns quads of 4 consecutive time points, i.e. 4*N consecutive output floats, which it
+// writes to the warp's staging buffer as N 16-byte vectors per array.  The env's whole pos / vel block ([T, N] floats
+// each) then leaves the SM as two TMA bulk stores (cp.async.bulk shared->global) issued by one lane: full lines, no
+// per-element global stores.  The next env's weights are prefetched before the current env is evaluated, and its
+// evaluation overlaps the drain of the bulk stores.
+#ifndef FG_TRAJ_MINB
+#define FG_TRAJ_MINB 2
+#endif
 template <int MP, int N, int KW>
-__global__ void __launch_bounds__(kTrajThreads)
+__global__ void __launch_bounds__(kTrajThreads, FG_TRAJ_MINB)
 k_trajgen_closed(const __grid_constant__ DevCfg c, const float* __restrict__ params, const float* __restrict__ bc_pos,
                  const float* __restrict__ bc_vel, float* __restrict__ pos_out, float* __restrict__ vel_out,
-                 const long long B) {
+                 const long long B, const int envs_per_block) {
   extern __shared__ __align__(128) float smem[];
-  const int T = c.T, K = c.K;
+  const int T = c.T;
   const int kw = (KW > 0) ? KW : c.cols_a;
-  const int RA = traj_row_stride(kw);
-  const int RB = (MP == FG_MP_PROMP) ? 1 : RA;
+  const int R4 = traj_r4(kw), REC4 = traj_rec4(MP, kw);
+  const int nq = (T + 3) >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* stage = smem;                                          // [warps][2][kTrajStageFloats]  (128-byte aligned)
-  float* tabA = stage + kTrajWarps * 2 * kTrajStageFloats;      // [T, RA]
-  float* tabB = tabA + T * RA;                                  // ProMP: [T-1] time increments; ProDMP: [T, RB]
-  float* tabR = tabB + ((c.rows_b * RB + 3) & ~3);              // ProMP: reciprocals of the increments
-  float* wgen = tabR + ((c.rows_b + 3) & ~3);                   // fallback only: [warps][N*kw]
-  for (int i = tid; i < T * RA; i += kTrajThreads) {
-    const int r = i / RA, col = i - r * RA;
-    tabA[i] = (col < kw) ? c.tab_a[r * kw + col] : 0.f;
-  }
-  for (int i = tid; i < c.rows_b * RB; i += kTrajThreads) {
-    const int r = i / RB, col = i - r * RB;
-    tabB[i] = (col < c.cols_b) ? c.tab_b[r * c.cols_b + col] : 0.f;
-  }
-  if constexpr (MP == FG_MP_PROMP)
-    for (int i = tid; i < c.rows_b; i += kTrajThreads) tabR[i] = __frcp_rn(c.tab_b[i]);
+  float* stage = smem;                                                      // [warps][2][kTrajStageFloats]
+  float4* rec = reinterpret_cast<float4*>(stage + kTrajWarps * 2 * kTrajStageFloats);   // [nq][REC4]
+  float* wgen = reinterpret_cast<float*>(rec + nq * REC4);                  // KW == 0 only: [warps][N * kw]
+
+  // ---- stage the quad records (packed once in fg_create; L2 resident) ----
+  for (int i = tid; i < nq * REC4; i += kTrajThreads) rec[i] = c.quad_rec[i];
   __syncthreads();
 
   float* tp = stage + warp * 2 * kTrajStageFloats;
   float* tv = tp + kTrajStageFloats;
-  const int KP = (MP == FG_MP_PROMP) ? K : K + 1;
+  float* wg = wgen + warp * N * kw;
+  // params per dof: compile-time when the column count is (immediate load offsets)
+  const int KP = (KW > 0) ? ((MP == FG_MP_PROMP) ? KW : KW - 2) : ((MP == FG_MP_PROMP) ? c.K : c.K + 1);
   const float r_tau = __frcp_rn(c.tau);
-  constexpr int STEP = (MP == FG_MP_PROMP) ? 31 : 32;
   constexpr int KWC = (KW > 0) ? KW : 1;
-  constexpr int RAC = (KW > 0) ? ((KW + 3) & ~3) : 4;
+  constexpr int R4C = (KW > 0) ? traj_r4(KW) : 1;
   const int TN = T * N;
-  const bool whole = TN <= kTrajStageFloats;          // stage the whole env, else one pass of rows at a time
-  const bool bulk = whole && (TN % 4 == 0);           // TMA needs 16-byte sizes / addresses
-  const long long warps_total = (long long)gridDim.x * kTrajWarps;
+  const bool bulk = (TN % 4 == 0);                    // TMA needs 16-byte sizes / addresses
+  const int chunk_rows = min(nq * 4, (kTrajStageFloats / (4 * N)) * 4);   // rows staged at a time (a multiple of 4)
+  // Work distribution: a block owns `envs_per_block` consecutive envs (its warps take them round-robin) and the grid
+  // is NOT persistent: the hardware block scheduler hands out blocks as SMs free up, which balances the two dies'
+  // different distance to the L2 slices (measured: statically partitioned persistent grids top out ~15 % lower in
+  // write bandwidth, profiles/README.md "store patterns").
+  const long long b_end = min(B, ((long long)blockIdx.x + 1) * envs_per_block);
+  constexpr long long warps_total = kTrajWarps;
   bool pending = false;                               // lane 0: a bulk store of this warp's stage is in flight
-  for (long long b = (long long)blockIdx.x * kTrajWarps + warp; b < B; b += warps_total) {
-    // per-env weight vector, identical in every lane (broadcast loads)
-    float w[N][KWC];
-    float* wg = wgen + warp * N * kw;
+
+  // per-env weight vector, identical in every lane (broadcast loads)
+  auto load_weights = [&](long long b, float (&w)[N][KWC]) {
 #pragma unroll
     for (int d = 0; d < N; ++d) {
       float yb = 0.f, vb = 0.f;
@@ -103,93 +99,135 @@ k_trajgen_closed(const __grid_constant__ DevCfg c, const float* __restrict__ par
         if constexpr (KW > 0) w[d][k] = x; else if (lane == 0) wg[d * kw + k] = x;
       }
     }
-    if (pending) {                      // the previous env's stage must have been read out before it is overwritten
-      bulk_wait_read0();
-      pending = false;
-    }
-    __syncwarp();
+  };
 
-    auto dot_row = [&](const float* row, int d) -> float {
+  long long b = (long long)blockIdx.x * envs_per_block + warp;
+  float w[N][KWC], wn[N][KWC];
+  if constexpr (KW > 0) {
+    if (b < b_end) load_weights(b, wn);
+  }
+  for (; b < b_end; b += warps_total) {
+    if constexpr (KW > 0) {
+#pragma unroll
+      for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int k = 0; k < KWC; ++k) w[d][k] = wn[d][k];
+      if (b + warps_total < b_end) load_weights(b + warps_total, wn);     // prefetch: in flight while this env is evaluated
+    } else {
+      __syncwarp();
+      load_weights(b, w);
+      __syncwarp();
+    }
+
+    // dot(table row, weights of dof d): FMA chain in index order, accumulator starts at 0 (oracle 'mirror' mode)
+    auto dot_row = [&](const float4* row, int d) -> float {
       float acc = 0.f;
       if constexpr (KW > 0) {
-        float r[RAC];
+        float r[R4C * 4];
 #pragma unroll
-        for (int j = 0; j < RAC / 4; ++j) {
-          const float4 x = reinterpret_cast<const float4*>(row)[j];
+        for (int j = 0; j < R4C; ++j) {
+          const float4 x = row[j];
           r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
         }
 #pragma unroll
         for (int k = 0; k < KWC; ++k) acc = fmaf(r[k], w[d][k], acc);
       } else {
-        for (int k = 0; k < kw; ++k) acc = fmaf(row[k], wg[d * kw + k], acc);
+        const float* rw = reinterpret_cast<const float*>(row);
+        for (int k = 0; k < kw; ++k) acc = fmaf(rw[k], wg[d * kw + k], acc);
       }
       return acc;
     };
 
     float* gp = pos_out + b * TN;
     float* gv = vel_out + b * TN;
-    for (int t0 = 0; t0 < T; t0 += STEP) {
-      const int t = t0 + lane;
-      float p0[N], vv[N];
-      const int tc = (t < T) ? t : T - 1;
-      const float* r0 = tabA + tc * RA;
-      if constexpr (MP == FG_MP_PROMP) {
-        const int tb = (t < T - 1) ? t : T - 2;
-        const float dtt = tabB[tb], rdt = tabR[tb];
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-          p0[d] = dot_row(r0, d);
-          const float pn = __shfl_down_sync(0xffffffffu, p0[d], 1);
-          vv[d] = div_by(__fsub_rn(pn, p0[d]), dtt, rdt);     // garbage on row T-1 (and lane 31): fixed up below
-        }
-      } else {
-        const float* rv = tabB + tc * RB;
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-          p0[d] = dot_row(r0, d);
-          vv[d] = div_by(dot_row(rv, d), c.tau, r_tau);
-        }
+    for (int c0 = 0; c0 < T; c0 += chunk_rows) {            // one chunk when the env fits the stage (T*N <= 1024)
+      const int rows = min(chunk_rows, T - c0);
+      if (pending) {                    // the previous bulk store must have read the stage before it is overwritten
+        bulk_wait_read0();
+        pending = false;
       }
-      const int rows = min(STEP, T - t0);
-      const int off = whole ? t0 * N : 0;
-      if (lane < rows) {
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-          tp[off + lane * N + d] = p0[d];
-          tv[off + lane * N + d] = vv[d];
-        }
-      }
-      if (!whole) {       // long trajectories: flush this pass with plain coalesced stores
-        __syncwarp();
-        if (MP == FG_MP_PROMP && t0 + rows == T && rows >= 2 && lane < N)
-          tv[(rows - 1) * N + lane] = tv[(rows - 2) * N + lane];
-        __syncwarp();
-        for (int i = lane; i < rows * N; i += 32) {
-          gp[t0 * N + i] = tp[i];
-          gv[t0 * N + i] = tv[i];
-        }
-        __syncwarp();
-      }
-    }
-    if (whole) {
       __syncwarp();
-      if (MP == FG_MP_PROMP && lane < N) tv[(T - 1) * N + lane] = tv[(T - 2) * N + lane];   // vel[T-1] = vel[T-2]
+      for (int q = (c0 >> 2) + lane; 4 * q < c0 + rows; q += 32) {
+        const float4* rq = rec + q * REC4;
+        float pv[4 * N], vv[4 * N];     // this quad's 4*N consecutive output floats
+        if constexpr (MP == FG_MP_PROMP) {
+          const float4 dt4 = rq[5 * R4], rd4 = rq[5 * R4 + 1];
+          const float dts[4] = {dt4.x, dt4.y, dt4.z, dt4.w}, rds[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
+          float prev[N];
+#pragma unroll
+          for (int d = 0; d < N; ++d) prev[d] = dot_row(rq, d);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+              const float nxt = dot_row(rq + (r + 1) * R4, d);
+              pv[r * N + d] = prev[d];
+              vv[r * N + d] = div_by(__fsub_rn(nxt, prev[d]), dts[r], rds[r]);   // row T-1 is fixed up below
+              prev[d] = nxt;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+              pv[r * N + d] = dot_row(rq + r * R4, d);
+              vv[r * N + d] = div_by(dot_row(rq + (4 + r) * R4, d), c.tau, r_tau);
+            }
+          }
+        }
+        const int off = (4 * q - c0) * N;
+        if (4 * q + 4 <= T) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            reinterpret_cast<float4*>(tp + off)[j] = make_float4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+            reinterpret_cast<float4*>(tv + off)[j] = make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
+          }
+        } else {                        // ragged tail (T not a multiple of 4)
+#pragma unroll
+          for (int j = 0; j < 4 * N; ++j)
+            if (4 * q + j / N < T) {
+              tp[off + j] = pv[j];
+              tv[off + j] = vv[j];
+            }
+        }
+      }
+      __syncwarp();
+      if (MP == FG_MP_PROMP && c0 + rows == T && lane < N) {          // vel[T-1] = vel[T-2]
+        float v2 = 0.f;
+        if (T - 2 >= c0) {
+          v2 = tv[(T - 2 - c0) * N + lane];
+        } else if (T >= 2) {            // T-2 sits in the previous chunk: re-evaluate it from the records
+          const int q2 = (T - 2) >> 2, r2 = (T - 2) & 3;
+          const float4* rq = rec + q2 * REC4;
+          const float dtt = reinterpret_cast<const float*>(rq + 5 * R4)[r2], rdt = reinterpret_cast<const float*>(rq + 5 * R4 + 1)[r2];
+          float a0 = 0.f, a1 = 0.f;
+          const float* x0 = reinterpret_cast<const float*>(rq + r2 * R4);
+          const float* x1 = reinterpret_cast<const float*>(rq + (r2 + 1) * R4);
+          for (int k = 0; k < kw; ++k) {
+            const float wk = params[b * N * KP + lane * KP + k];
+            a0 = fmaf(x0[k], wk, a0);
+            a1 = fmaf(x1[k], wk, a1);
+          }
+          v2 = div_by(__fsub_rn(a1, a0), dtt, rdt);
+        }
+        tv[(T - 1 - c0) * N + lane] = v2;
+      }
       if (bulk) {
         fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the async (TMA) proxy
         __syncwarp();
         if (lane == 0) {
-          bulk_store_s2g(gp, tp, (unsigned)(TN * sizeof(float)));
-          bulk_store_s2g(gv, tv, (unsigned)(TN * sizeof(float)));
+          bulk_store_s2g(gp + c0 * N, tp, (unsigned)(rows * N * sizeof(float)));
+          bulk_store_s2g(gv + c0 * N, tv, (unsigned)(rows * N * sizeof(float)));
           bulk_commit();
           pending = true;
         }
       } else {
         __syncwarp();
-        for (int i = lane; i < TN; i += 32) {
-          gp[i] = tp[i];
-          gv[i] = tv[i];
+        for (int i = lane; i < rows * N; i += 32) {
+          gp[c0 * N + i] = tp[i];
+          gv[c0 * N + i] = tv[i];
         }
-        __syncwarp();
       }
     }
   }
