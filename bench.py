@@ -385,7 +385,7 @@ def main():
                     vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"{ENV_ID}, {B} envs per GPU (BASELINE configs[1]), one fused rollout launch per step",
                                 envs_per_gpu=B, n_params=N_PARAMS, sigma=args.sigma, max_episode_steps=200,
-                                contexts="device Philox sampler", parallelism=f"env-shard x{world}",
+                                contexts="device sampler (numpy-exact PCG64 streams, fg_reset)", parallelism=f"env-shard x{world}",
                                 l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
                                 collective="all_gather(return,length,flags) per step" if world > 1 else "none"),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B),

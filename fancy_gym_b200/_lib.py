@@ -49,10 +49,28 @@ class FgRolloutIO(C.Structure):
     ]
 
 
+class FgResetCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("env_kind", C.c_int32), ("n_dof", C.c_int32), ("random_start", C.c_int32), ("time_aware", C.c_int32),
+        ("fixed", C.c_double * 4), ("has_fixed", C.c_int32 * 4),
+        ("n_obs_out", C.c_int32), ("obs_index", C.c_int32 * FG_MAX_OBS),
+    ]
+
+
+class FgResetIO(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("seeds", C.c_void_p), ("seed0", C.c_int64), ("reseed", C.c_int32), ("rng_state", C.c_void_p),
+        ("q", C.c_void_p), ("v", C.c_void_p), ("steps", C.c_void_p), ("done", C.c_void_p), ("ctx", C.c_void_p),
+        ("obs", C.c_void_p),
+    ]
+
+
 # every symbol include/fancy_gym_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "fg_last_error", "fg_abi_version", "fg_create", "fg_destroy", "fg_num_params", "fg_obs_full_dim",
-    "fg_rollout", "fg_trajgen", "fg_ffma_probe",
+    "fg_rollout", "fg_trajgen", "fg_reset", "fg_ffma_probe",
 ]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfancygym_b200.so")
@@ -83,6 +101,8 @@ def _load():
     lib.fg_trajgen.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_void_p]
     lib.fg_trajgen.restype = C.c_int
+    lib.fg_reset.argtypes = [C.POINTER(FgResetCfg), C.POINTER(FgResetIO), C.c_int64, C.c_void_p]
+    lib.fg_reset.restype = C.c_int
     lib.fg_ffma_probe.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     lib.fg_ffma_probe.restype = C.c_int
     return lib

@@ -71,6 +71,7 @@ class BlackBoxWrapper(Wrapper):
         self.plan_steps = 0
         self.wall_mode = int(wall_mode)
         self._interface_checked = False
+        self._fast_reset = self._can_fast_reset()
 
         # ---- device side ----
         base = self.env.unwrapped
@@ -80,18 +81,51 @@ class BlackBoxWrapper(Wrapper):
         self.traj_gen.device = self.device
         B, n = self.num_envs, base.n_links
         dev = self.device
-        self._ret = torch.zeros(B, dtype=torch.float64, device=dev)
-        self._len = torch.zeros(B, dtype=torch.int32, device=dev)
-        self._flags = torch.zeros(B, dtype=torch.uint8, device=dev)
-        self._info = torch.zeros(B, 4, dtype=torch.float64, device=dev)
+        # Two sets of result buffers used alternately: what step() returns stays valid until the step after the next
+        # one, without a device-side copy per call.
+        self._obs_index_np = np.asarray(self._obs_index())
+        self._out_sets = [dict(ret=torch.zeros(B, dtype=torch.float64, device=dev),
+                               len=torch.zeros(B, dtype=torch.int32, device=dev),
+                               flags=torch.zeros(B, dtype=torch.uint8, device=dev),
+                               info=torch.zeros(B, 4, dtype=torch.float64, device=dev),
+                               obs=torch.zeros(B, len(self._obs_index_np), dtype=torch.float32, device=dev))
+                          for _ in range(2)]
+        self._out_i = 0
+        self._obs_index_dev = None
+        self._bind_outputs()
         self._cond_pos = torch.zeros(B, n, dtype=torch.float32, device=dev)
         self._cond_vel = torch.zeros(B, n, dtype=torch.float32, device=dev)
-        self._obs = None
         self._handles: Dict[Any, C.c_void_p] = {}
         self._lo = torch.as_tensor(self.traj_gen_action_space.low, device=dev)
         self._hi = torch.as_tensor(self.traj_gen_action_space.high, device=dev)
         self._has_finite_bounds = bool(np.isfinite(self.traj_gen_action_space.low).any()
                                        or np.isfinite(self.traj_gen_action_space.high).any())
+
+    def _can_fast_reset(self) -> bool:
+        """True when reset() of every wrapper between this one and the step env is the plain pass-through (or the
+        time-aware column, which fg_reset writes itself) and the env samples on the device"""
+        from ..utils.wrappers import TimeAwareObservation
+        base = self.env.unwrapped
+        if not hasattr(base, "device_reset") or getattr(base, "context_sampler", None) != "device":
+            return False
+        layer = self.env
+        while layer is not base:
+            if type(layer).reset is not Wrapper.reset and not isinstance(layer, TimeAwareObservation):
+                return False
+            layer = layer.env
+        return True
+
+    def _bind_outputs(self):
+        o = self._out_sets[self._out_i]
+        self._ret, self._len, self._flags, self._info, self._obs = o["ret"], o["len"], o["flags"], o["info"], o["obs"]
+
+    def _flip_outputs(self):
+        """next result set; the "unbounded" HoleReacher reward keeps per-episode state in info[:, 2:4] (fg_rollout_io.info)"""
+        prev = self._info
+        self._out_i ^= 1
+        self._bind_outputs()
+        if getattr(self._base, "rew_fct", None) == "unbounded":
+            self._info[:, 2:4] = prev[:, 2:4]
 
     # ---- spaces (black_box_wrapper.py:122-148) --------------------------------------------------
     def _get_traj_gen_action_space(self):
@@ -120,7 +154,9 @@ class BlackBoxWrapper(Wrapper):
 
     def observation(self, observation):
         if self.return_context_observation:
-            observation = observation[..., torch.as_tensor(self._obs_index(), device=observation.device)]
+            if self._obs_index_dev is None:
+                self._obs_index_dev = torch.as_tensor(self._obs_index_np, device=observation.device)
+            observation = observation[..., self._obs_index_dev]
         return observation.to(torch.float32)
 
     # ---- kernel handle for the current plan -----------------------------------------------------
@@ -156,7 +192,7 @@ class BlackBoxWrapper(Wrapper):
         cfg.rew_fct = int(getattr(base, "rew_fct_code", 0))
         cfg.wall_mode = self.wall_mode
         cfg.time_aware = int(self._time_aware())
-        idx = self._obs_index()
+        idx = self._obs_index_np
         cfg.n_obs_out = len(idx)
         for j, i in enumerate(idx):
             cfg.obs_index[j] = int(i)
@@ -237,8 +273,7 @@ class BlackBoxWrapper(Wrapper):
         B = self.num_envs
         T = self.traj_gen.n_steps
         h = self._handle()
-        if self._obs is None or self._obs.shape[1] != len(self._obs_index()):
-            self._obs = torch.zeros(B, len(self._obs_index()), dtype=torch.float32, device=self.device)
+        self._flip_outputs()
         io = _lib.FgRolloutIO()
         io.struct_size = C.sizeof(_lib.FgRolloutIO)
         io.params = params.data_ptr()
@@ -280,23 +315,23 @@ class BlackBoxWrapper(Wrapper):
             self.condition_set = True      # every live env breaks at the same step or is done
 
         self.current_traj_steps += seg     # live envs all advance by `seg`; finished envs are frozen
-        length = self._len.clone()
+        length = self._len
         flags = self._flags
         terminated = (flags & _lib.FLAG_TERMINATED) != 0
         truncated = (flags & _lib.FLAG_TRUNCATED) != 0
-        ret = self._ret.clone()
+        ret = self._ret
         if self.reward_aggregation is np.mean:
             ret = ret / length.clamp(min=1)
         infos: Dict[str, Any] = {}
         if base.env_kind in (_lib.ENV_HOLE_REACHER, _lib.ENV_VIAPOINT_REACHER):
             infos["is_success"] = (flags & _lib.FLAG_SUCCESS) != 0
             infos["is_collided"] = (flags & _lib.FLAG_COLLIDED) != 0
-            infos["end_effector"] = self._info[:, 0:2].clone()
+            infos["end_effector"] = self._info[:, 0:2]
             if getattr(base, "rew_fct", None) == "unbounded":        # hr_unbounded_reward.py:53-56
                 infos["joints"] = base.q.clone()
         elif base.env_kind == _lib.ENV_SIMPLE_REACHER:
-            infos["reward_dist"] = self._info[:, 0].clone()
-            infos["reward_ctrl"] = self._info[:, 1].clone()
+            infos["reward_dist"] = self._info[:, 0]
+            infos["reward_ctrl"] = self._info[:, 1]
         if need_rewards and self.reward_aggregation not in (np.sum, np.mean, sum):
             r = dbg["rewards"].cpu().numpy()
             ln = length.cpu().numpy()
@@ -308,7 +343,7 @@ class BlackBoxWrapper(Wrapper):
             infos["step_observations"] = dbg["obs"]
             infos["step_rewards"] = dbg["rewards"]
         infos["trajectory_length"] = length
-        obs = self._obs.clone()
+        obs = self._obs
         return self._format(obs, ret, terminated, truncated, infos, as_numpy, scalar)
 
     def _planned_trajectory(self, local_params):
@@ -353,9 +388,16 @@ class BlackBoxWrapper(Wrapper):
         self.plan_steps = 0
         self.traj_gen.reset()
         self.condition_set = False
-        obs, info = self.env.reset(seed=seed, options=options)
-        obs = self.observation(obs)
-        self._obs = obs.clone().contiguous()
+        base = self._base
+        if self._fast_reset and not {k for k in (options or {}) if k != "as_numpy"}:
+            # one kernel: numpy-exact context sampling + state reset + context observation (fg_reset)
+            self._flip_outputs()
+            obs, info = base.device_reset(seed, obs_index=self._obs_index_np, time_aware=self._time_aware(), out=self._obs), {}
+        else:
+            obs, info = self.env.reset(seed=seed, options={k: v for k, v in (options or {}).items() if k != "as_numpy"} or None)
+            self._flip_outputs()
+            self._obs.copy_(self.observation(obs))
+            obs = self._obs
         as_numpy = (options or {}).get("as_numpy", self.num_envs == 1)
         if as_numpy:
             obs = obs.cpu().numpy()

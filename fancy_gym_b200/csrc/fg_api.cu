@@ -10,6 +10,7 @@
 #include "fancy_gym_b200.h"
 #include "fg_device.cuh"
 #include "fg_dispatch.h"
+#include "fg_reset.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -206,6 +207,37 @@ fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_po
   if (prev != h->device) cudaSetDevice(prev);
   if (why) return fail(FG_ERR_UNSUPPORTED, "fg_trajgen: %s", why);
   if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_trajgen launch: %s", cudaGetErrorString(e));
+  return FG_OK;
+}
+
+fg_status fg_reset(const fg_reset_cfg* cfg, const fg_reset_io* io, int64_t B, void* stream) {
+  if (!cfg || !io) return fail(FG_ERR_INVALID, "fg_reset: null argument");
+  if (cfg->struct_size != sizeof(fg_reset_cfg) || io->struct_size != sizeof(fg_reset_io))
+    return fail(FG_ERR_INVALID, "fg_reset: struct_size mismatch (ABI)");
+  if (cfg->env_kind < FG_ENV_HOLE_REACHER || cfg->env_kind > FG_ENV_SIMPLE_REACHER)
+    return fail(FG_ERR_INVALID, "fg_reset: env_kind %d has no reset sampler", cfg->env_kind);
+  if (cfg->n_dof < 1 || cfg->n_dof > FG_MAX_DOF) return fail(FG_ERR_INVALID, "fg_reset: n_dof %d out of range", cfg->n_dof);
+  if (cfg->n_obs_out < 0 || cfg->n_obs_out > FG_MAX_OBS) return fail(FG_ERR_INVALID, "fg_reset: n_obs_out out of range");
+  const int extra[3] = {4, 5, 3};
+  const int n_full = 3 * cfg->n_dof + extra[cfg->env_kind] + (cfg->time_aware ? 1 : 0);
+  for (int j = 0; j < cfg->n_obs_out; ++j)
+    if (cfg->obs_index[j] < 0 || cfg->obs_index[j] >= n_full)
+      return fail(FG_ERR_INVALID, "fg_reset: obs_index[%d]=%d outside the %d-wide observation", j, cfg->obs_index[j], n_full);
+  if (B < 0) return fail(FG_ERR_INVALID, "fg_reset: negative batch");
+  if (B == 0) return FG_OK;
+  if (!io->rng_state || !io->q || !io->v || !io->steps || !io->done || !io->ctx)
+    return fail(FG_ERR_INVALID, "fg_reset: a required buffer is NULL");
+  if (cfg->n_obs_out > 0 && !io->obs) return fail(FG_ERR_INVALID, "fg_reset: obs buffer is NULL");
+  fg::ResetCfg c;
+  memset(&c, 0, sizeof(c));
+  c.env_kind = cfg->env_kind; c.n_dof = cfg->n_dof; c.random_start = cfg->random_start; c.time_aware = cfg->time_aware;
+  for (int i = 0; i < 4; ++i) { c.fixed[i] = cfg->fixed[i]; c.has_fixed[i] = cfg->has_fixed[i]; }
+  c.n_obs_out = cfg->n_obs_out;
+  for (int j = 0; j < cfg->n_obs_out; ++j) c.obs_index[j] = cfg->obs_index[j];
+  const unsigned blocks = (unsigned)((B + 127) / 128);
+  fg::k_reset<<<blocks, 128, 0, (cudaStream_t)stream>>>(c, *io, B);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_reset launch: %s", cudaGetErrorString(e));
   return FG_OK;
 }
 

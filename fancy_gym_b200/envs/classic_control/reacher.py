@@ -9,11 +9,12 @@ sampling:
   SimpleReacherEnv    fancy_gym/envs/classic_control/simple_reacher/simple_reacher.py
   (base: base_reacher/base_reacher.py, base_reacher_direct.py, base_reacher_torque.py)
 
-reset(seed=s) seeds env i with s + i (gymnasium's vector-env convention).  With
-context_sampler='numpy' (default) every env draws its context from
-Generator(PCG64(SeedSequence(seed_i))) in the reference's draw order, so env i is the reference env
-reset with seed s + i.  context_sampler='device' draws the same distributions with torch's Philox
-generator on the GPU (for large batches; not stream-compatible with numpy).
+reset(seed=s) seeds env i with s + i (gymnasium's vector-env convention); env i then is the reference
+env reset with seed s + i: its context comes from Generator(PCG64(SeedSequence(seed_i))) in the
+reference's draw order.  context_sampler='device' (default) runs that sampler as ONE CUDA kernel
+(fg_reset: PCG64 / SeedSequence restated in integer arithmetic, per-env stream state kept in HBM for
+unseeded resets); context_sampler='numpy' is the same sampling done with numpy on the host (a cross-check
+for tests, O(num_envs) Python).
 """
 from __future__ import annotations
 
@@ -36,7 +37,7 @@ class BaseReacherEnv(Env):
     n_ctx_obs = 0            # task-specific obs entries between velocity and step counter
 
     def __init__(self, n_links: int, random_start: bool = True, allow_self_collision: bool = False,
-                 num_envs: int = 1, device: Union[str, torch.device, None] = None, context_sampler: str = "numpy",
+                 num_envs: int = 1, device: Union[str, torch.device, None] = None, context_sampler: str = "device",
                  render_mode: Optional[str] = None, **kwargs):
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
@@ -65,7 +66,7 @@ class BaseReacherEnv(Env):
         self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
         self.ctx = torch.zeros(B, 4, dtype=torch.float64, device=dev)
         self._seed_rngs = None
-        self._torch_gen = None
+        self._rng_state = None            # [B, 5] uint64 PCG64 stream state of the device sampler
         self._was_reset = False
 
     def _batch_or_none(self):
@@ -112,9 +113,6 @@ class BaseReacherEnv(Env):
     def _sample_numpy(self, seeds) -> Dict[str, np.ndarray]:
         raise NotImplementedError
 
-    def _sample_device(self, gen) -> Dict[str, torch.Tensor]:
-        raise NotImplementedError
-
     def reset(self, *, seed=None, options: Optional[Dict[str, Any]] = None):
         """-> (obs [B, O] float32 tensor on the device, {}).  options['contexts'] (dict of arrays)
         bypasses sampling; options['random_start'] as in base_reacher.py:77-80."""
@@ -132,11 +130,7 @@ class BaseReacherEnv(Env):
                 self._seed_rngs = rngs
             c = {k: torch.as_tensor(v, dtype=torch.float64) for k, v in self._sample_numpy(rngs, seeds, random_start).items()}
         else:
-            if seed is not None or self._torch_gen is None:
-                self._torch_gen = torch.Generator(device=dev)
-                self._torch_gen.manual_seed(int(np.asarray(seed).reshape(-1)[0]) if seed is not None
-                                            else int(np.random.SeedSequence().entropy % (2 ** 62)))
-            c = self._sample_device(self._torch_gen, random_start)
+            return self.device_reset(seed, random_start=random_start), {}
         q0 = c.pop("q0").to(dev)
         self.q.zero_()
         self.q[:, 0] = q0
@@ -149,6 +143,58 @@ class BaseReacherEnv(Env):
 
     def _set_ctx(self, c):
         raise NotImplementedError
+
+    def _fixed_context(self):
+        """(values[4], given[4]) of the constructor-fixed task context, laid out like `ctx`"""
+        return [0.0] * 4, [0] * 4
+
+    def device_reset(self, seed=None, obs_index=None, time_aware=False, random_start=None, out=None):
+        """fg_reset: one kernel samples the contexts (numpy-exact streams), resets the state buffers and writes the
+        observation columns `obs_index` of the reset state (default: the full step observation)."""
+        import ctypes as C
+        B, n, dev = self.num_envs, self.n_links, self.device
+        n_full = self.observation_space.shape[0] + (1 if time_aware else 0)
+        idx = list(range(n_full)) if obs_index is None else [int(i) for i in obs_index]
+        cfg = _lib.FgResetCfg()
+        cfg.struct_size = C.sizeof(_lib.FgResetCfg)
+        cfg.env_kind, cfg.n_dof = self.env_kind, n
+        cfg.random_start = int(bool(self.random_start if random_start is None else random_start))
+        cfg.time_aware = int(bool(time_aware))
+        vals, given = self._fixed_context()
+        for i in range(4):
+            cfg.fixed[i], cfg.has_fixed[i] = float(vals[i]), int(given[i])
+        cfg.n_obs_out = len(idx)
+        for j, i in enumerate(idx):
+            cfg.obs_index[j] = i
+        io = _lib.FgResetIO()
+        io.struct_size = C.sizeof(_lib.FgResetIO)
+        seeds_dev = None
+        if seed is None and self._rng_state is not None:
+            io.reseed = 0
+        else:
+            io.reseed = 1
+            if seed is None:       # first unseeded reset: OS entropy, like np_random(None)
+                io.seed0 = int(np.random.SeedSequence().entropy % (2 ** 62))
+            else:
+                seeds = np.asarray(seed).reshape(-1)
+                if seeds.size == 1:
+                    io.seed0 = int(seeds[0])
+                elif seeds.size == B:
+                    seeds_dev = torch.as_tensor(seeds.astype(np.int64), device=dev)
+                    io.seeds = seeds_dev.data_ptr()
+                else:
+                    raise ValueError(f"need one seed or {B} seeds")
+            if self._rng_state is None:
+                self._rng_state = torch.zeros(B, 5, dtype=torch.int64, device=dev)
+        io.rng_state = self._rng_state.data_ptr()
+        io.q, io.v, io.steps, io.done, io.ctx = (self.q.data_ptr(), self.v.data_ptr(), self.steps.data_ptr(),
+                                                 self.done.data_ptr(), self.ctx.data_ptr())
+        obs = out if out is not None else torch.empty(B, len(idx), dtype=torch.float32, device=dev)
+        io.obs = obs.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib.fg_reset(C.byref(cfg), C.byref(io), B, C.c_void_p(stream)))
+        self._was_reset = True
+        return obs
 
     def _first_joint(self, rng, random_start):
         # base_reacher.py:81-86 (random start angle of the first joint, the arm is straight)
@@ -203,18 +249,10 @@ class HoleReacherEnv(BaseReacherEnv):
             out["q0"][i] = self._first_joint(rng, random_start)
         return out
 
-    def _sample_device(self, gen, random_start):
-        B, dev = self.num_envs, self.device
-        u = torch.rand(B, 4, generator=gen, device=dev, dtype=torch.float64)
-        width = 0.15 + 0.35 * u[:, 0] if self.initial_width is None else torch.full((B,), float(self.initial_width), device=dev, dtype=torch.float64)
-        if self.initial_x is None:
-            direction = torch.where(u[:, 1] < 0.5, -1.0, 1.0)
-            x = direction * (width / 2 + (3.5 - width / 2) * u[:, 2])
-        else:
-            x = torch.full((B,), float(self.initial_x), device=dev, dtype=torch.float64)
-        depth = torch.full((B,), 1.0 if self.initial_depth is None else float(self.initial_depth), device=dev, dtype=torch.float64)
-        q0 = np.pi / 4 + (np.pi / 2) * u[:, 3] if random_start else torch.full((B,), self._start_pos[0], device=dev, dtype=torch.float64)
-        return dict(x=x, width=width, depth=depth, q0=q0)
+    def _fixed_context(self):
+        given = [self.initial_x is not None, self.initial_width is not None, self.initial_depth is not None, 0]
+        vals = [self.initial_x or 0.0, self.initial_width or 0.0, self.initial_depth or 0.0, 0.0]
+        return vals, given
 
     def _set_ctx(self, c):
         self.ctx.zero_()
@@ -271,26 +309,12 @@ class ViaPointReacherEnv(BaseReacherEnv):
             self._first_joint(rngs[i], random_start)
         return out
 
-    def _sample_device(self, gen, random_start):
-        B, dev, total = self.num_envs, self.device, float(self.n_links)
-
-        def ring(lo, hi, half):
-            out = torch.empty(B, 2, device=dev, dtype=torch.float64)
-            todo = torch.ones(B, dtype=torch.bool, device=dev)
-            while bool(todo.any()):
-                cand = (torch.rand(B, 2, generator=gen, device=dev, dtype=torch.float64) * 2 - 1) * half
-                nrm = cand.norm(dim=1)
-                ok = todo & (nrm < hi) & (nrm > lo)
-                out[ok] = cand[ok]
-                todo &= ~ok
-            return out
-        via = ring(-1.0, 0.5 * total, 0.5 * total) if self.initial_via_target is None else \
-            torch.as_tensor(np.asarray(self.initial_via_target, dtype=np.float64), device=dev).expand(B, 2)
-        goal = ring(0.5 * total, total, total) if self.intitial_target is None else \
-            torch.as_tensor(np.asarray(self.intitial_target, dtype=np.float64), device=dev).expand(B, 2)
-        q0 = np.pi / 4 + (np.pi / 2) * torch.rand(B, generator=gen, device=dev, dtype=torch.float64) if random_start \
-            else torch.full((B,), self._start_pos[0], device=dev, dtype=torch.float64)
-        return dict(via=via, goal=goal, q0=q0)
+    def _fixed_context(self):
+        via, tgt = self.initial_via_target, self.intitial_target
+        given = [via is not None] * 2 + [tgt is not None] * 2
+        vals = list(np.asarray(via if via is not None else (0, 0), dtype=np.float64)) + \
+            list(np.asarray(tgt if tgt is not None else (0, 0), dtype=np.float64))
+        return vals, given
 
     def _set_ctx(self, c):
         self.ctx[:, 0:2] = c["via"]
@@ -337,21 +361,10 @@ class SimpleReacherEnv(BaseReacherEnv):
             self._first_joint(rngs[i], random_start)
         return out
 
-    def _sample_device(self, gen, random_start):
-        B, dev, total = self.num_envs, self.device, float(self.n_links)
-        if self.inital_target is None:
-            goal = torch.empty(B, 2, device=dev, dtype=torch.float64)
-            todo = torch.ones(B, dtype=torch.bool, device=dev)
-            while bool(todo.any()):
-                cand = (torch.rand(B, 2, generator=gen, device=dev, dtype=torch.float64) * 2 - 1) * total
-                ok = todo & (cand.norm(dim=1) < total)
-                goal[ok] = cand[ok]
-                todo &= ~ok
-        else:
-            goal = torch.as_tensor(np.asarray(self.inital_target, dtype=np.float64), device=dev).expand(B, 2)
-        q0 = np.pi / 4 + (np.pi / 2) * torch.rand(B, generator=gen, device=dev, dtype=torch.float64) if random_start \
-            else torch.zeros(B, device=dev, dtype=torch.float64)
-        return dict(goal=goal, q0=q0)
+    def _fixed_context(self):
+        tgt = self.inital_target
+        vals = list(np.asarray(tgt if tgt is not None else (0, 0), dtype=np.float64)) + [0.0, 0.0]
+        return vals, [tgt is not None] * 2 + [0, 0]
 
     def _set_ctx(self, c):
         self.ctx.zero_()

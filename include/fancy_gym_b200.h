@@ -154,6 +154,37 @@ typedef struct fg_rollout_io {
   double* dbg_rewards;     /* [B, T] infos['step_rewards'] */
 } fg_rollout_io;
 
+/* Episode reset of the classic_control reachers on the device (replaces the host-side samplers
+ * hole_reacher.py:60-112, viapoint_reacher.py:45-77, simple_reacher.py:46-96, base_reacher.py:73-93). */
+typedef struct fg_reset_cfg {
+  uint32_t struct_size;
+  int32_t env_kind;            /* FG_ENV_HOLE_REACHER / _VIAPOINT_REACHER / _SIMPLE_REACHER */
+  int32_t n_dof;
+  int32_t random_start;        /* constructor kwarg random_start (base_reacher.py:77-86) */
+  int32_t time_aware;          /* append the (zero) elapsed-time column to the observation */
+  /* fixed task context (constructor kwargs hole_x, hole_width, hole_depth | via_target, target | target);
+   * has_fixed[i] == 0: entry i is sampled.  Layout as fg_rollout_io.ctx. */
+  double fixed[4];
+  int32_t has_fixed[4];
+  int32_t n_obs_out;           /* observation compaction as in fg_config */
+  int32_t obs_index[FG_MAX_OBS];
+} fg_reset_cfg;
+
+typedef struct fg_reset_io {
+  uint32_t struct_size;
+  const int64_t* seeds;        /* [B] per-env seeds (DEVICE) or NULL: env i uses seed0 + i */
+  int64_t seed0;
+  int32_t reseed;              /* 1: every env starts the numpy stream Generator(PCG64(SeedSequence(seed_i)));
+                                  0: continue the streams stored in rng_state (reset(seed=None)) */
+  uint64_t* rng_state;         /* [B, 5] in/out: PCG64 state hi, lo, increment hi, lo, buffered uint32 (bit 32 = valid) */
+  double* q;                   /* outputs: as fg_rollout_io */
+  double* v;
+  int32_t* steps;
+  uint8_t* done;
+  double* ctx;                 /* [B, 4] */
+  float* obs;                  /* [B, n_obs_out] observation of the reset state, or NULL */
+} fg_reset_io;
+
 typedef struct fg_handle fg_handle;
 
 const char* fg_last_error(void);
@@ -185,6 +216,12 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
  */
 fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_pos, const float* bc_vel,
                      float* pos_out, float* vel_out, int64_t B, void* stream);
+
+/*
+ * Resets B envs: samples the task context and the start pose with numpy-exact streams (env i == the reference env
+ * reset with seed_i), zeroes velocities / step counters / done flags and writes the context observation.
+ */
+fg_status fg_reset(const fg_reset_cfg* cfg, const fg_reset_io* io, int64_t B, void* stream);
 
 /*
  * FP32 FFMA-chain microbenchmark used as the roofline denominator of the fused rollout

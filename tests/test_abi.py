@@ -32,10 +32,15 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
     prog = tmp_path / "layout.c"
     fields_cfg = [f[0] for f in _lib.FgConfig._fields_]
     fields_io = [f[0] for f in _lib.FgRolloutIO._fields_]
+    fields_rc = [f[0] for f in _lib.FgResetCfg._fields_]
+    fields_ri = [f[0] for f in _lib.FgResetIO._fields_]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){',
-             'printf("fg_config %zu\\n", sizeof(fg_config));', 'printf("fg_rollout_io %zu\\n", sizeof(fg_rollout_io));']
+             'printf("fg_config %zu\\n", sizeof(fg_config));', 'printf("fg_rollout_io %zu\\n", sizeof(fg_rollout_io));',
+             'printf("fg_reset_cfg %zu\\n", sizeof(fg_reset_cfg));', 'printf("fg_reset_io %zu\\n", sizeof(fg_reset_io));']
     lines += [f'printf("fg_config.{f} %zu\\n", offsetof(fg_config, {f}));' for f in fields_cfg]
     lines += [f'printf("fg_rollout_io.{f} %zu\\n", offsetof(fg_rollout_io, {f}));' for f in fields_io]
+    lines += [f'printf("fg_reset_cfg.{f} %zu\\n", offsetof(fg_reset_cfg, {f}));' for f in fields_rc]
+    lines += [f'printf("fg_reset_io.{f} %zu\\n", offsetof(fg_reset_io, {f}));' for f in fields_ri]
     lines += ['return 0;}']
     prog.write_text("\n".join(lines))
     exe = tmp_path / "layout"
@@ -43,6 +48,11 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
     out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     assert int(out["fg_config"]) == C.sizeof(_lib.FgConfig)
     assert int(out["fg_rollout_io"]) == C.sizeof(_lib.FgRolloutIO)
+    assert int(out["fg_reset_cfg"]) == C.sizeof(_lib.FgResetCfg) and int(out["fg_reset_io"]) == C.sizeof(_lib.FgResetIO)
+    for f in fields_rc:
+        assert int(out[f"fg_reset_cfg.{f}"]) == getattr(_lib.FgResetCfg, f).offset, f
+    for f in fields_ri:
+        assert int(out[f"fg_reset_io.{f}"]) == getattr(_lib.FgResetIO, f).offset, f
     for f in fields_cfg:
         assert int(out[f"fg_config.{f}"]) == getattr(_lib.FgConfig, f).offset, f
     for f in fields_io:

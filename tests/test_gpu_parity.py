@@ -237,3 +237,47 @@ def test_zero_params_keep_the_arm_still():
     assert bool((info["trajectory_length"] == 200).all()) and not bool(te.any()) and bool(tr.all())
     want = -((ee0 - goal) ** 2).sum(1)
     assert torch.allclose(ret, want, rtol=1e-12, atol=0)
+
+
+# --------------------------------------------------------------------------------------------
+# device-side reset (fg_reset): numpy-exact context streams
+# --------------------------------------------------------------------------------------------
+RESET_CASES = [("fancy/HoleReacher-v0", {}), ("fancy/HoleReacher-v0", dict(hole_x=1.0, random_start=False)),
+               ("fancy/HoleReacher-v0", dict(hole_width=0.3, hole_depth=None)),
+               ("fancy/ViaPointReacher-v0", {}), ("fancy/ViaPointReacher-v0", dict(random_start=True, target=(3.0, 2.0))),
+               ("fancy/SimpleReacher-v0", {}), ("fancy/SimpleReacher-v0", dict(random_start=False)),
+               ("fancy/LongSimpleReacher-v0", dict(target=(1.0, -2.0)))]
+
+
+@pytest.mark.parametrize("env_id,kw", RESET_CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(RESET_CASES)])
+def test_device_reset_reproduces_numpy_streams(env_id, kw):
+    """env i reset with seed s on the device == numpy's Generator(PCG64(SeedSequence(s + i))) in the reference's draw order
+    (bit-exact contexts and start angles), also for explicit per-env seeds, 64-bit seeds and unseeded follow-up resets
+    that continue the per-env streams."""
+    fancy_gym = _fg()
+    B = 1000
+    dev = fancy_gym.make(env_id, num_envs=B, device="cuda:0", context_sampler="device", **kw)
+    ref = fancy_gym.make(env_id, num_envs=B, device="cuda:0", context_sampler="numpy", **kw)
+    rng = np.random.default_rng(0)
+    for seed in (0, 12345, rng.integers(0, 2**62, size=B), None, None, 2**40 + 17, None):
+        o_dev, _ = dev.reset(seed=seed)
+        o_ref, _ = ref.reset(seed=seed)
+        assert torch.equal(dev.ctx, ref.ctx), seed
+        assert torch.equal(dev.q, ref.q), seed
+        assert float(dev.v.abs().max()) == 0.0 and int(dev.steps.abs().max()) == 0 and int(dev.done.max()) == 0
+        assert torch.allclose(o_dev, o_ref, rtol=0, atol=1e-6)
+
+
+def test_blackbox_reset_fast_path_matches_wrapper_chain():
+    fancy_gym = _fg()
+    B = 513
+    for env_id, bbk in (("fancy_ProMP/HoleReacher-v0", {}), ("fancy_DMP/ViaPointReacher-v0", {}),
+                        ("fancy_ProDMP/SimpleReacher-v0", {"replanning_schedule": lambda p, v, o, a, t: t % 25 == 0})):
+        over = {"black_box_kwargs": bbk}
+        fast = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override=over)
+        slow = fancy_gym.make(env_id, num_envs=B, device="cuda:0", context_sampler="numpy", mp_config_override=over)
+        assert fast._fast_reset and not slow._fast_reset
+        a, _ = fast.reset(seed=5)
+        b, _ = slow.reset(seed=5)
+        assert a.shape == b.shape == (B, fast.observation_space.shape[0])
+        assert torch.allclose(a, b, rtol=0, atol=1e-6)
