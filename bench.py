@@ -98,6 +98,7 @@ class ClockSampler:
         self.sm, self.power, self.mask = [], [], 0
         self.sm_max = None
         self._stop = threading.Event()
+        self._ready = threading.Event()      # set after the first sample: NVML init / imports must not land in a timed region
         self._th = None
         self.err = None
 
@@ -122,13 +123,16 @@ class ClockSampler:
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
                 self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self._ready.set()
                 self._stop.wait(0.02)
         except Exception as e:      # noqa: BLE001
             self.err = repr(e)
+        self._ready.set()
 
     def __enter__(self):
         self._th = threading.Thread(target=self._loop, daemon=True)
         self._th.start()
+        self._ready.wait(timeout=10)
         return self
 
     def __exit__(self, *a):
@@ -264,6 +268,7 @@ def main():
         sync_all()
         t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
         t_start.record()
+        host_t0 = time.perf_counter()
         for i in range(K):
             s = sets[(W + i) % n_sets]
             load_state(s)
@@ -275,6 +280,7 @@ def main():
                 dist.all_gather_into_tensor(gathered, pack)
             total_steps += env._len.sum()
         t_end.record()
+        host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K     # host time to ISSUE one step (no sync inside)
         sync_all()
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
@@ -321,15 +327,15 @@ def main():
     for i in range(3):
         env.traj_gen._run_trajgen(out=outs[i % 2])
     torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    a.record()
+    reps = 20
+    tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for i in range(reps):
+        tev[i][0].record()
         env.traj_gen._run_trajgen(out=outs[i % 2])
-    b.record()
+        tev[i][1].record()
     torch.cuda.synchronize(dev)
     del outs
-    traj_ms = a.elapsed_time(b) / reps
+    traj_ms = sum(a.elapsed_time(b) for a, b in tev) / reps        # average launch duration over the timed launches
     traj_gbs = Bt * TRAJ_BYTES_PER_ENV / (traj_ms * 1e-3) / 1e9
     roofline_traj = dict(bound="hbm", achieved=traj_gbs, peak=hbm_peak, unit="GB/s", frac=traj_gbs / hbm_peak, traffic=None,
                          kernel="k_trajgen_closed<PROMP,5,5>", kernel_ms=traj_ms, peak_source=hbm_src,
@@ -376,7 +382,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_sample(2, sigma=args.sigma)
+        cpu = cpu_reference_sample(6, sigma=args.sigma)
         cpu["scalar_port_value"] = cpu_reference_sample(2, batch=1, sigma=args.sigma)["value"]
 
     if rank == 0:
@@ -388,7 +394,7 @@ def main():
                                 contexts="device sampler (numpy-exact PCG64 streams, fg_reset)", parallelism=f"env-shard x{world}",
                                 l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
                                 collective="all_gather(return,length,flags) per step" if world > 1 else "none"),
-                    episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B),
+                    episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e,
                     clocks=clk.summary(), gpu_launches=K)
         print(json.dumps(line))
