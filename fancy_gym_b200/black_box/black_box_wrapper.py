@@ -84,12 +84,16 @@ class BlackBoxWrapper(Wrapper):
         # Two sets of result buffers used alternately: what step() returns stays valid until the step after the next
         # one, without a device-side copy per call.
         self._obs_index_np = np.asarray(self._obs_index())
-        self._out_sets = [dict(ret=torch.zeros(B, dtype=torch.float64, device=dev),
-                               len=torch.zeros(B, dtype=torch.int32, device=dev),
-                               flags=torch.zeros(B, dtype=torch.uint8, device=dev),
-                               info=torch.zeros(B, 4, dtype=torch.float64, device=dev),
-                               obs=torch.zeros(B, len(self._obs_index_np), dtype=torch.float32, device=dev))
-                          for _ in range(2)]
+        # (return | length | flags) of a step live in ONE contiguous byte block: the multi-GPU exchange is a single
+        # all-gather of that block, with no packing kernels (fancy_gym_b200/dist).
+        from ..dist import result_block_bytes, result_block_views
+        self._out_sets = []
+        for _ in range(2):
+            block = torch.zeros(result_block_bytes(B), dtype=torch.uint8, device=dev)
+            r, ln, fl = result_block_views(block, B)
+            self._out_sets.append(dict(block=block, ret=r, len=ln, flags=fl,
+                                       info=torch.zeros(B, 4, dtype=torch.float64, device=dev),
+                                       obs=torch.zeros(B, len(self._obs_index_np), dtype=torch.float32, device=dev)))
         self._out_i = 0
         self._obs_index_dev = None
         self._bind_outputs()
@@ -118,6 +122,7 @@ class BlackBoxWrapper(Wrapper):
     def _bind_outputs(self):
         o = self._out_sets[self._out_i]
         self._ret, self._len, self._flags, self._info, self._obs = o["ret"], o["len"], o["flags"], o["info"], o["obs"]
+        self._result_block = o["block"]
 
     def _flip_outputs(self):
         """next result set; the "unbounded" HoleReacher reward keeps per-episode state in info[:, 2:4] (fg_rollout_io.info)"""

@@ -76,3 +76,32 @@ def gather_episode_results(ret, length, flags, total_envs: Optional[int] = None,
     if min(sizes) != width:
         out = torch.cat([out[r * width:r * width + sizes[r]] for r in range(world)], dim=0)
     return unpack_results(out)
+
+
+# ---- zero-copy variant: the black-box wrapper keeps (return f64 | length i32 | flags u8) of a step in ONE contiguous
+# ---- byte block, so the per-step exchange is a single collective on that block with no packing kernels -------------
+def result_block_bytes(num_envs: int) -> int:
+    """bytes of one result block, padded to 16 so that typed views of the gathered blocks stay aligned"""
+    return (13 * num_envs + 15) // 16 * 16
+
+
+def result_block_views(block: torch.Tensor, num_envs: int):
+    """(ret f64 [.., B], length i32 [.., B], flags u8 [.., B]) views of one block [nbytes] or of gathered blocks [W, nbytes]"""
+    B = num_envs
+    lead = block.shape[:-1]
+    ret = block[..., :8 * B].view(torch.float64)
+    length = block[..., 8 * B:12 * B].view(torch.int32)
+    flags = block[..., 12 * B:13 * B]
+    return ret.reshape(*lead, B), length.reshape(*lead, B), flags.reshape(*lead, B)
+
+
+def all_gather_result_blocks(block: torch.Tensor, out: Optional[torch.Tensor] = None, group=None):
+    """ONE all-gather of every rank's result block -> [world, nbytes] (rank-major = global env order for even shards).
+    Identity ([1, nbytes] view) without a process group."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return block[None]
+    world = dist.get_world_size(group)
+    if out is None:
+        out = block.new_empty(world * block.numel())
+    dist.all_gather_into_tensor(out, block, group=group)
+    return out.view(world, block.numel())

@@ -69,3 +69,42 @@ def test_gather_is_identity_without_process_group():
     ret, ln, fl = torch.ones(3, dtype=torch.float64), torch.ones(3, dtype=torch.int32), torch.ones(3, dtype=torch.uint8)
     a, b, c = gather_episode_results(ret, ln, fl)
     assert a is ret and b is ln and c is fl
+
+
+def _block_worker(rank, world, port, B, q):
+    from fancy_gym_b200.dist import all_gather_result_blocks, result_block_bytes, result_block_views
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(rank)
+        block = torch.zeros(result_block_bytes(B), dtype=torch.uint8)
+        ret, length, flags = result_block_views(block, B)
+        ret.copy_(torch.as_tensor(rng.standard_normal(B))); length.copy_(torch.as_tensor(rng.integers(1, 201, B).astype(np.int32)))
+        flags.copy_(torch.as_tensor(rng.integers(0, 16, B).astype(np.uint8)))
+        g_ret, g_len, g_flags = result_block_views(all_gather_result_blocks(block), B)
+        ok = g_ret.shape == (world, B)
+        for r in range(world):
+            rr = np.random.default_rng(r)
+            ok &= bool(np.array_equal(g_ret[r].numpy(), rr.standard_normal(B)))
+            ok &= bool(np.array_equal(g_len[r].numpy(), rr.integers(1, 201, B).astype(np.int32)))
+            ok &= bool(np.array_equal(g_flags[r].numpy(), rr.integers(0, 16, B).astype(np.uint8)))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [64, 37])
+def test_result_blocks_gather_world2(B):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_block_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
