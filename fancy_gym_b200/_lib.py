@@ -70,7 +70,7 @@ class FgResetIO(C.Structure):
 # every symbol include/fancy_gym_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "fg_last_error", "fg_abi_version", "fg_create", "fg_destroy", "fg_num_params", "fg_obs_full_dim",
-    "fg_rollout", "fg_trajgen", "fg_reset", "fg_ffma_probe",
+    "fg_rollout", "fg_trajgen", "fg_reset", "fg_traj_cov", "fg_traj_cov_work_floats", "fg_ffma_probe",
 ]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfancygym_b200.so")
@@ -101,6 +101,11 @@ def _load():
     lib.fg_trajgen.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_void_p]
     lib.fg_trajgen.restype = C.c_int
+    lib.fg_traj_cov_work_floats.argtypes = [C.c_void_p, C.c_int64]
+    lib.fg_traj_cov_work_floats.restype = C.c_int64
+    lib.fg_traj_cov.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_int64, C.c_void_p]
+    lib.fg_traj_cov.restype = C.c_int
     lib.fg_reset.argtypes = [C.POINTER(FgResetCfg), C.POINTER(FgResetIO), C.c_int64, C.c_void_p]
     lib.fg_reset.restype = C.c_int
     lib.fg_ffma_probe.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]

@@ -210,6 +210,41 @@ fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_po
   return FG_OK;
 }
 
+int64_t fg_traj_cov_work_floats(const fg_handle* h, int64_t B) {
+  if (!h || B < 0) return -1;
+  return B * (int64_t)h->cfg.n_dof * h->cfg.n_steps + B + 1;
+}
+
+fg_status fg_traj_cov(const fg_handle* h, const float* params_L, float reg, int32_t reg_scope, float* cov_out,
+                      float* std_out, float* work, int32_t path, int64_t B, void* stream) {
+  if (!h || !params_L || !work) return fail(FG_ERR_INVALID, "fg_traj_cov: null argument");
+  if (h->cfg.mp_kind != FG_MP_PROMP && h->cfg.mp_kind != FG_MP_PRODMP)
+    return fail(FG_ERR_INVALID, "fg_traj_cov: only the probabilistic MPs (ProMP, ProDMP) have a trajectory covariance");
+  if (!cov_out && !std_out) return fail(FG_ERR_INVALID, "fg_traj_cov: neither cov_out nor std_out given");
+  if (path < 0 || path > 2) return fail(FG_ERR_INVALID, "fg_traj_cov: path %d unknown", path);
+  if (B < 0) return fail(FG_ERR_INVALID, "fg_traj_cov: negative batch");
+  if (B == 0) return FG_OK;
+  fg::CovArgs a;
+  memset(&a, 0, sizeof(a));
+  a.basis = h->d_tab_a;
+  a.ld = h->dev.cols_a;
+  a.c0 = (h->cfg.mp_kind == FG_MP_PRODMP) ? 2 : 0;      // ProDMP tables start with the two boundary-condition columns
+  a.Kc = h->dev.cols_a - a.c0;
+  a.T = h->cfg.n_steps; a.N = h->cfg.n_dof;
+  a.L = params_L; a.cov = cov_out; a.stdv = std_out;
+  a.diag = work; a.envmax = work + B * (int64_t)a.N * a.T; a.gmax = a.envmax + B;
+  a.reg = reg; a.batch_scope = reg_scope ? 1 : 0;
+  int prev = 0;
+  FG_CUDA(cudaGetDevice(&prev));
+  if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));
+  const char* why = nullptr;
+  cudaError_t e = fg::launch_traj_cov(a, B, path == 0 ? 1 : path, (cudaStream_t)stream, h->max_smem_optin, &why);
+  if (prev != h->device) cudaSetDevice(prev);
+  if (why) return fail(FG_ERR_UNSUPPORTED, "fg_traj_cov: %s", why);
+  if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_traj_cov launch: %s", cudaGetErrorString(e));
+  return FG_OK;
+}
+
 fg_status fg_reset(const fg_reset_cfg* cfg, const fg_reset_io* io, int64_t B, void* stream) {
   if (!cfg || !io) return fail(FG_ERR_INVALID, "fg_reset: null argument");
   if (cfg->struct_size != sizeof(fg_reset_cfg) || io->struct_size != sizeof(fg_reset_io))

@@ -15,6 +15,23 @@ cudaError_t launch_trajgen(const DevCfg& c, int mp_kind, const float* params, co
                            float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
                            int sm_count, const char** why);
 
+// trajectory covariance (fg_cov.cu); path 1 = CUDA cores, 2 = tcgen05
+struct CovArgs {
+  const float* basis;   // device [T, ld] float32, columns c0 .. c0+Kc-1 are Bm
+  int ld, c0, Kc, T, N; // N = dof
+  const float* L;       // [B, D, D]
+  float* cov;           // [B, N*T, N*T] or null
+  float* stdv;          // [B, T, N] or null
+  float* diag;          // scratch [B, N*T]
+  float* envmax;        // scratch [B]
+  float* gmax;          // scratch [1]
+  float reg;
+  int batch_scope;      // 1: regulariser uses the max over the whole batch (mp_pytorch's torch.max over the batched tensor)
+  int rows_per_block;
+};
+
+cudaError_t launch_traj_cov(const CovArgs& a, long long B, int path, cudaStream_t stream, int max_smem_optin, const char** why);
+
 // per-env translation units (compiled in parallel)
 #define FG_DECL_ENV_LAUNCH(name)                                                                              \
   cudaError_t name(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,        \

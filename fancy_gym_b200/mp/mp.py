@@ -181,6 +181,48 @@ class MPInterface:
                                        C.c_void_p(stream)))
         return (pos, vel) if batched else (pos[0], vel[0])
 
+    # ---- trajectory covariance of the probabilistic MPs (fg_traj_cov; mp_pytorch: set_mp_params_variances,
+    # ---- get_traj_pos_cov, get_traj_pos_std — no call site inside fancy_gym) ----------------
+    probabilistic = False
+
+    def set_mp_params_variances(self, params_L):
+        """params_L [B, D, D] (or [D, D]): lower-triangular Cholesky factor of the weight covariance, D = num_dof * Kc"""
+        if not self.probabilistic:
+            raise NotImplementedError(f"{type(self).__name__} is not a probabilistic MP")
+        self.params_L = None if params_L is None else torch.as_tensor(params_L)
+
+    def _run_traj_cov(self, want_cov, want_std, reg=1e-4, batch_scope=False, path=0):
+        if getattr(self, "params_L", None) is None:
+            raise RuntimeError("set_mp_params_variances() must be called first")
+        L = self.params_L.to(self.device, torch.float32)
+        batched = L.dim() == 3
+        if not batched:
+            L = L[None]
+        L = L.contiguous()
+        B, T, N = L.shape[0], self.n_steps, self.num_dof
+        D = self._num_local_params
+        if L.shape[1:] != (D, D):
+            raise ValueError(f"params_L must be [.., {D}, {D}], got {tuple(L.shape)}")
+        h = self._trajgen_handle()
+        cov = torch.empty(B, N * T, N * T, device=self.device, dtype=torch.float32) if want_cov else None
+        std = torch.empty(B, T, N, device=self.device, dtype=torch.float32) if want_std else None
+        work = torch.empty(int(_lib.lib.fg_traj_cov_work_floats(h, B)), device=self.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib.fg_traj_cov(h, L.data_ptr(), float(reg), int(bool(batch_scope)),
+                                        cov.data_ptr() if want_cov else None, std.data_ptr() if want_std else None,
+                                        work.data_ptr(), int(path), B, C.c_void_p(stream)))
+        if not batched:
+            cov, std = (cov[0] if want_cov else None), (std[0] if want_std else None)
+        return cov, std
+
+    def get_traj_pos_cov(self, reg: float = 1e-4, batch_scope: bool = False, path: int = 0):
+        """[.., dof*T, dof*T] float32, dof-major rows / columns (d * T + t)"""
+        return self._run_traj_cov(True, False, reg, batch_scope, path)[0]
+
+    def get_traj_pos_std(self, reg: float = 1e-4, batch_scope: bool = False):
+        """[.., T, dof]: sqrt of the regularised covariance diagonal (the full matrix is never materialised)"""
+        return self._run_traj_cov(False, True, reg, batch_scope)[1]
+
     def get_traj_pos(self):
         return self._run_trajgen()[0]
 
@@ -199,6 +241,7 @@ class ProMP(MPInterface):
     """pos = (weights_scale * Phi) W^T, vel = forward finite difference over the float32 time grid,
     last row duplicated."""
     mp_kind = _lib.MP_PROMP
+    probabilistic = True
 
     @property
     def _num_local_params(self):
@@ -243,6 +286,7 @@ class ProDMP(MPInterface):
     """Closed-form DMP solution with boundary conditions (App. B.7):
     pos = xi1 y_b + xi2 tau dy_b + H_pos [w; g],  vel = (xi3 y_b + xi4 tau dy_b + H_vel [w; g]) / tau."""
     mp_kind = _lib.MP_PRODMP
+    probabilistic = True
 
     def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, auto_scale_basis=False,
                  relative_goal=False, disable_weights=False, disable_goal=False, **kwargs):

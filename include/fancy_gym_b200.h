@@ -218,6 +218,21 @@ fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_po
                      float* pos_out, float* vel_out, int64_t B, void* stream);
 
 /*
+ * Trajectory covariance of the probabilistic MPs — replaces mp_pytorch's ProMP / ProDMP get_traj_pos_cov() /
+ * get_traj_pos_std() behind the traj_gen object (no call site inside fancy_gym):
+ *   Sigma_y = Psi (L L^T) Psi^T + reg * max(diag) * I,   Psi = blockdiag over dof of the handle's basis [T, Kc]
+ * with Kc = n_basis (ProMP) or n_basis + 1 (ProDMP: weights and goal).  Rows / columns are dof-major (d * T + t).
+ *   params_L  [B, D, D], D = n_dof * Kc: lower-triangular Cholesky factor of the weight covariance (upper part ignored)
+ *   cov_out   [B, n_dof*T, n_dof*T] or NULL;  std_out [B, T, n_dof] or NULL (sqrt of the regularised diagonal)
+ *   work      [fg_traj_cov_work_floats(h, B)] float scratch
+ *   reg_scope 0: max over each env's own diagonal; 1: max over the whole batch (what mp_pytorch does on a batched tensor)
+ *   path      0: automatic; 1: CUDA cores; 2: tcgen05 tensor cores (3xTF32 split, TMEM accumulators)
+ */
+int64_t fg_traj_cov_work_floats(const fg_handle* h, int64_t B);
+fg_status fg_traj_cov(const fg_handle* h, const float* params_L, float reg, int32_t reg_scope, float* cov_out,
+                      float* std_out, float* work, int32_t path, int64_t B, void* stream);
+
+/*
  * Resets B envs: samples the task context and the start pose with numpy-exact streams (env i == the reference env
  * reset with seed_i), zeroes velocities / step counters / done flags and writes the context observation.
  */

@@ -673,3 +673,27 @@ def get_trajectory_generator(trajectory_generator_type, action_dim, basis_genera
     if t == "prodmp":
         return ProDMP(basis_generator, action_dim, **kwargs)
     raise ValueError(f"Specified movement primitive type {t} not supported")
+
+
+# ----------------------------------------------------------------------------------------------
+# trajectory covariance (App. B.5) — PARITY UNPINNED: mp_pytorch is absent and fancy_gym never calls it
+def traj_pos_cov(basis, params_L, num_dof, reg=1e-4, batch_scope=False):
+    """Sigma_y = Psi (L L^T) Psi^T + reg * max(diag Sigma_y) * I in float64.
+    basis [T, Kc] (already scaled: weights_scale * Phi for ProMP, the bracketed H = [H_w | H_g] for ProDMP),
+    params_L [B, D, D] with D = num_dof * Kc (lower triangle used), rows / columns dof-major (d * T + t).
+    Returns (cov [B, dof*T, dof*T], std [B, T, dof]); the max is per env unless batch_scope (mp_pytorch takes torch.max
+    over whatever batch it is given; the reference never batches)."""
+    basis = np.asarray(basis, dtype=F64)
+    L = np.tril(np.asarray(params_L, dtype=F64))
+    T, Kc = basis.shape
+    B = L.shape[0]
+    psi = np.zeros((num_dof * T, num_dof * Kc))
+    for d in range(num_dof):
+        psi[d * T:(d + 1) * T, d * Kc:(d + 1) * Kc] = basis
+    sigma_w = L @ np.swapaxes(L, -1, -2)
+    cov = psi[None] @ sigma_w @ psi.T[None]
+    diag = np.einsum("bii->bi", cov)
+    mx = diag.max() if batch_scope else diag.max(axis=1)[:, None, None]
+    cov = cov + reg * mx * np.eye(num_dof * T)[None]
+    std = np.sqrt(np.einsum("bii->bi", cov)).reshape(B, num_dof, T).transpose(0, 2, 1)
+    return cov, std
