@@ -61,7 +61,7 @@ class FgResetCfg(C.Structure):
 class FgResetIO(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32),
-        ("seeds", C.c_void_p), ("seed0", C.c_int64), ("reseed", C.c_int32), ("rng_state", C.c_void_p),
+        ("seeds", C.c_void_p), ("seed0", C.c_int64), ("reseed", C.c_int32), ("rng_state", C.c_void_p), ("mask", C.c_void_p),
         ("q", C.c_void_p), ("v", C.c_void_p), ("steps", C.c_void_p), ("done", C.c_void_p), ("ctx", C.c_void_p),
         ("obs", C.c_void_p),
     ]

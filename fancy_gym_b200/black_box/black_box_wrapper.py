@@ -410,6 +410,21 @@ class BlackBoxWrapper(Wrapper):
                 obs = obs[0]
         return obs, info
 
+    def reset_done(self, mask=None):
+        """Auto-reset for vector-env use: starts a new episode in every env whose last step ended one (or where `mask`
+        is set), continuing each env's own context stream, in one fg_reset launch.  Returns the observation of ALL envs
+        (rows of envs that were not reset are unchanged).  Only meaningful when every env plans on the same schedule,
+        i.e. without replanning / sub-trajectories (there a finished env waits for reset())."""
+        if not self._fast_reset:
+            raise NotImplementedError("reset_done() needs the device-side sampler (context_sampler='device')")
+        if self.do_replanning or self.learn_sub_trajectories:
+            raise NotImplementedError("partial resets are not defined while envs share one replanning clock")
+        if mask is None:
+            mask = self._base.done
+        obs = self._obs.clone()
+        self._base.device_reset(None, obs_index=self._obs_index_np, time_aware=self._time_aware(), out=obs, mask=mask)
+        return obs
+
     def close(self):
         for h in self._handles.values():
             _lib.lib.fg_destroy(h)

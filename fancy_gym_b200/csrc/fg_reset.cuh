@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(128)
 k_reset(const __grid_constant__ ResetCfg c, const __grid_constant__ fg_reset_io io, const long long B) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (io.mask && !io.mask[b]) return;
   const int N = c.n_dof;
   const double total = (double)N;      // link lengths are all 1 (base_reacher.py:19)
   Pcg64 g;

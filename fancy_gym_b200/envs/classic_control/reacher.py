@@ -148,7 +148,7 @@ class BaseReacherEnv(Env):
         """(values[4], given[4]) of the constructor-fixed task context, laid out like `ctx`"""
         return [0.0] * 4, [0] * 4
 
-    def device_reset(self, seed=None, obs_index=None, time_aware=False, random_start=None, out=None):
+    def device_reset(self, seed=None, obs_index=None, time_aware=False, random_start=None, out=None, mask=None):
         """fg_reset: one kernel samples the contexts (numpy-exact streams), resets the state buffers and writes the
         observation columns `obs_index` of the reset state (default: the full step observation)."""
         import ctypes as C
@@ -187,6 +187,9 @@ class BaseReacherEnv(Env):
             if self._rng_state is None:
                 self._rng_state = torch.zeros(B, 5, dtype=torch.int64, device=dev)
         io.rng_state = self._rng_state.data_ptr()
+        if mask is not None:       # partial reset: only envs with mask != 0 (their rows of `out` are rewritten, the rest kept)
+            mask = mask.to(dev, torch.uint8).contiguous()
+            io.mask = mask.data_ptr()
         io.q, io.v, io.steps, io.done, io.ctx = (self.q.data_ptr(), self.v.data_ptr(), self.steps.data_ptr(),
                                                  self.done.data_ptr(), self.ctx.data_ptr())
         obs = out if out is not None else torch.empty(B, len(idx), dtype=torch.float32, device=dev)

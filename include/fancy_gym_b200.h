@@ -177,6 +177,7 @@ typedef struct fg_reset_io {
   int32_t reseed;              /* 1: every env starts the numpy stream Generator(PCG64(SeedSequence(seed_i)));
                                   0: continue the streams stored in rng_state (reset(seed=None)) */
   uint64_t* rng_state;         /* [B, 5] in/out: PCG64 state hi, lo, increment hi, lo, buffered uint32 (bit 32 = valid) */
+  const uint8_t* mask;         /* [B] or NULL: only envs with mask != 0 are reset (vector-env auto-reset of finished envs) */
   double* q;                   /* outputs: as fg_rollout_io */
   double* v;
   int32_t* steps;

@@ -225,3 +225,42 @@ def test_max_planning_times(fg, mp_type, max_planning_times, sub_segment_steps, 
         planning_times += 1
         assert planning_times <= 50
     assert planning_times == max_planning_times
+
+
+# ---- vector-env adapter ----------------------------------------------------------------------
+def test_vector_env_autoreset_continues_each_env_stream(fg):
+    """BlackBoxVectorEnv.step auto-resets every finished sub-env; sub-env i then is the reference env after
+    reset(seed=s+i) followed by an unseeded reset() — checked against the host-side numpy sampler."""
+    import torch
+    N = 257
+    vec = fg.make_vec("fancy_ProMP/HoleReacher-v0", N, device=DEV)
+    ref = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=N, device=DEV, context_sampler="numpy")
+    obs, _ = vec.reset(seed=3)
+    r_obs, _ = ref.reset(seed=3, options={"as_numpy": True})
+    assert obs.shape == (N, 18) and np.allclose(obs, r_obs, atol=1e-6)
+    rng = np.random.default_rng(0)
+    for it in range(3):
+        act = (0.5 * rng.standard_normal((N, 25))).astype(np.float32)
+        obs, rew, term, trunc, info = vec.step(act)
+        _, r_rew, r_term, r_trunc, r_info = ref.step(act)
+        assert np.array_equal(term, r_term) and np.array_equal(trunc, r_trunc) and np.allclose(rew, r_rew, rtol=1e-12)
+        assert np.array_equal(info["trajectory_length"], r_info["trajectory_length"])
+        assert (term | trunc).all() and info["_final_observation"].all()
+        r_obs, _ = ref.reset(seed=None, options={"as_numpy": True})       # the reference's unseeded follow-up reset
+        assert np.allclose(obs, r_obs, atol=1e-6), it
+        assert torch.equal(vec.env.unwrapped.ctx, ref.unwrapped.ctx)
+    vec.close()
+
+
+def test_partial_reset_only_touches_masked_envs(fg):
+    import torch
+    env = fg.make("fancy_DMP/ViaPointReacher-v0", num_envs=64, device=DEV)
+    env.reset(seed=0)
+    base = env.unwrapped
+    ctx0, q0 = base.ctx.clone(), base.q.clone()
+    mask = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    mask[::3] = 1
+    env.reset_done(mask)
+    keep = mask == 0
+    assert torch.equal(base.ctx[keep], ctx0[keep]) and torch.equal(base.q[keep], q0[keep])
+    assert not torch.equal(base.ctx[~keep], ctx0[~keep])
