@@ -67,10 +67,18 @@ class FgResetIO(C.Structure):
     ]
 
 
+class FgPhaseBasis(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("phase_kind", C.c_int32), ("alpha_phase", C.c_double),
+        ("n_basis_total", C.c_int32), ("first_learnable", C.c_int32),
+        ("centers", C.c_double * 16), ("bandwidth", C.c_double * 16),
+    ]
+
+
 # every symbol include/fancy_gym_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "fg_last_error", "fg_abi_version", "fg_create", "fg_destroy", "fg_num_params", "fg_obs_full_dim",
-    "fg_rollout", "fg_trajgen", "fg_reset", "fg_traj_cov", "fg_traj_cov_work_floats", "fg_ffma_probe",
+    "fg_rollout", "fg_trajgen", "fg_trajgen_phase", "fg_reset", "fg_traj_cov", "fg_traj_cov_work_floats", "fg_ffma_probe",
 ]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfancygym_b200.so")
@@ -101,6 +109,8 @@ def _load():
     lib.fg_trajgen.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_void_p]
     lib.fg_trajgen.restype = C.c_int
+    lib.fg_trajgen_phase.argtypes = [C.c_void_p, C.POINTER(FgPhaseBasis)] + [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]
+    lib.fg_trajgen_phase.restype = C.c_int
     lib.fg_traj_cov_work_floats.argtypes = [C.c_void_p, C.c_int64]
     lib.fg_traj_cov_work_floats.restype = C.c_int64
     lib.fg_traj_cov.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

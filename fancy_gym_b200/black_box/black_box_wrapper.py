@@ -71,6 +71,7 @@ class BlackBoxWrapper(Wrapper):
         self.plan_steps = 0
         self.wall_mode = int(wall_mode)
         self._interface_checked = False
+        self._traj_buf = None
         self._fast_reset = self._can_fast_reset()
 
         # ---- device side ----
@@ -175,13 +176,20 @@ class BlackBoxWrapper(Wrapper):
         for i in range(self._base.n_links):
             cfg.p_gains[i], cfg.d_gains[i] = float(p[i]), float(d[i])
 
-    def _handle(self):
+    def _handle(self, from_trajectory: bool = False):
+        """kernel handle of the current plan; `from_trajectory`: the desired trajectory comes from HBM (FG_MP_TRAJ), used
+        when the phase is per env (learned tau / delay) and fg_trajgen_phase has produced it"""
         tg, base = self.traj_gen, self._base
-        key = tg.table_key()
+        key = ("traj", tg.n_steps) if from_trajectory else tg.table_key()
         h = self._handles.get(key)
         if h is not None:
             return h
-        tb = tg.tables()
+        if from_trajectory:
+            from ..mp.mp import MPTables
+            tb = MPTables(mp_kind=_lib.MP_TRAJ, n_basis=0, n_steps=tg.n_steps, tab_a=np.zeros(1, np.float32),
+                          tab_b=np.zeros(1, np.float32))
+        else:
+            tb = tg.tables()
         cfg = _lib.FgConfig()
         cfg.struct_size = C.sizeof(_lib.FgConfig)
         cfg.env_kind, cfg.mp_kind = base.env_kind, tb.mp_kind
@@ -277,11 +285,22 @@ class BlackBoxWrapper(Wrapper):
         base = self._base
         B = self.num_envs
         T = self.traj_gen.n_steps
-        h = self._handle()
+        per_env_phase = not self.traj_gen.phase_gn.uniform()
+        if per_env_phase:
+            # learned tau / delay differ per env: fg_trajgen_phase evaluates the basis per env, the fused rollout then
+            # tracks that trajectory from HBM (8 KB per env, far below its compute time)
+            if self._traj_buf is None or self._traj_buf[0].shape[1] != T:
+                n = base.n_links
+                self._traj_buf = (torch.empty(B, T, n, dtype=torch.float32, device=self.device),
+                                  torch.empty(B, T, n, dtype=torch.float32, device=self.device))
+            self._planned_trajectory(params, out=self._traj_buf)
+        h = self._handle(from_trajectory=per_env_phase)
         self._flip_outputs()
         io = _lib.FgRolloutIO()
         io.struct_size = C.sizeof(_lib.FgRolloutIO)
         io.params = params.data_ptr()
+        if per_env_phase:
+            io.traj_pos, io.traj_vel = self._traj_buf[0].data_ptr(), self._traj_buf[1].data_ptr()
         io.ctx = base.ctx.data_ptr()
         io.q, io.v, io.steps, io.done = base.q.data_ptr(), base.v.data_ptr(), base.steps.data_ptr(), base.done.data_ptr()
         io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
@@ -351,13 +370,13 @@ class BlackBoxWrapper(Wrapper):
         obs = self._obs
         return self._format(obs, ret, terminated, truncated, infos, as_numpy, scalar)
 
-    def _planned_trajectory(self, local_params):
+    def _planned_trajectory(self, local_params, out=None):
         tg = self.traj_gen
         saved = tg.params
         tg.params = local_params
         if self.condition_set:
             tg.set_initial_conditions(tg.init_time, self._cond_pos, self._cond_vel)
-        pos, vel = tg._run_trajgen()
+        pos, vel = tg._run_trajgen(out=out)
         tg.params = saved
         return pos, vel
 

@@ -210,6 +210,41 @@ fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_po
   return FG_OK;
 }
 
+fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const float* times, const float* tau,
+                           const float* delay, const float* params, const float* bc_pos, const float* bc_vel,
+                           float* pos_out, float* vel_out, int64_t B, void* stream) {
+  if (!h || !pb || !times || !tau || !delay || !params || !pos_out || !vel_out)
+    return fail(FG_ERR_INVALID, "fg_trajgen_phase: null argument");
+  if (pb->struct_size != sizeof(fg_phase_basis)) return fail(FG_ERR_INVALID, "fg_trajgen_phase: struct_size mismatch (ABI)");
+  if (h->cfg.mp_kind != FG_MP_PROMP && h->cfg.mp_kind != FG_MP_DMP)
+    return fail(FG_ERR_UNSUPPORTED, "fg_trajgen_phase: per-env tau / delay is implemented for ProMP and DMP "
+                                    "(ProDMP's pre-integrated bases depend on tau)");
+  if (h->cfg.mp_kind == FG_MP_DMP && (!bc_pos || !bc_vel)) return fail(FG_ERR_INVALID, "fg_trajgen_phase: DMP needs boundary conditions");
+  if (pb->n_basis_total < 1 || pb->n_basis_total > 16 || pb->first_learnable < 0 ||
+      pb->first_learnable + h->cfg.n_basis > pb->n_basis_total)
+    return fail(FG_ERR_INVALID, "fg_trajgen_phase: basis counts inconsistent (total %d, first %d, weighted %d)",
+                pb->n_basis_total, pb->first_learnable, h->cfg.n_basis);
+  if (B < 0) return fail(FG_ERR_INVALID, "fg_trajgen_phase: negative batch");
+  if (B == 0) return FG_OK;
+  fg::PhaseArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mp_kind = h->cfg.mp_kind; a.N = h->cfg.n_dof; a.T = h->cfg.n_steps; a.K = h->cfg.n_basis;
+  a.phase_kind = pb->phase_kind; a.n_total = pb->n_basis_total; a.first = pb->first_learnable; a.alpha_phase = pb->alpha_phase;
+  for (int k = 0; k < 16; ++k) { a.cen[k] = pb->centers[k]; a.bw[k] = pb->bandwidth[k]; }
+  a.wscale = h->cfg.weights_scale; a.gscale = h->cfg.goal_scale; a.alpha = h->cfg.dmp_alpha; a.beta = h->cfg.dmp_alpha / 4.0f;
+  a.times = times; a.dts = h->d_tab_b; a.tau = tau; a.delay = delay; a.params = params; a.bc_pos = bc_pos; a.bc_vel = bc_vel;
+  a.pos = pos_out; a.vel = vel_out;
+  int prev = 0;
+  FG_CUDA(cudaGetDevice(&prev));
+  if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));
+  const char* why = nullptr;
+  cudaError_t e = fg::launch_trajgen_phase(a, B, (cudaStream_t)stream, h->max_smem_optin, &why);
+  if (prev != h->device) cudaSetDevice(prev);
+  if (why) return fail(FG_ERR_UNSUPPORTED, "fg_trajgen_phase: %s", why);
+  if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_trajgen_phase launch: %s", cudaGetErrorString(e));
+  return FG_OK;
+}
+
 int64_t fg_traj_cov_work_floats(const fg_handle* h, int64_t B) {
   if (!h || B < 0) return -1;
   return B * (int64_t)h->cfg.n_dof * h->cfg.n_steps + B + 1;

@@ -32,6 +32,26 @@ struct CovArgs {
 
 cudaError_t launch_traj_cov(const CovArgs& a, long long B, int path, cudaStream_t stream, int max_smem_optin, const char** why);
 
+// trajectory generation with a per-env phase (fg_trajgen_phase.cu)
+struct PhaseArgs {
+  int mp_kind, N, T, K;             // K weighted basis functions per dof
+  int phase_kind, n_total, first;   // phase 0 linear / 1 exp; RBF count incl. zero padding; first weighted RBF
+  double alpha_phase;
+  double cen[16], bw[16];
+  float wscale, gscale, alpha, beta;
+  const float* times;               // [T] float32 time grid (device)
+  const float* dts;                 // [T-1] its increments (ProMP velocity), device
+  const float* tau;                 // [B]
+  const float* delay;               // [B]
+  const float* params;              // [B, N * (K or K+1)]
+  const float* bc_pos;              // [B, N] (DMP)
+  const float* bc_vel;
+  float* pos;                       // [B, T, N]
+  float* vel;
+};
+
+cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t stream, int max_smem_optin, const char** why);
+
 // per-env translation units (compiled in parallel)
 #define FG_DECL_ENV_LAUNCH(name)                                                                              \
   cudaError_t name(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,        \

@@ -102,8 +102,10 @@ class MPInterface:
         self.dt = float(dt)
         if duration is None:     # learn_sub_trajectories: trajectory length follows the learned tau
             if not self.phase_gn.uniform():
-                tau = self.phase_gn.tau
-                if not bool((tau == tau.flatten()[0]).all()):
+                # one plan length per launch: the batch must agree on round(tau / dt) (this reads tau back to the host)
+                tau = self.phase_gn.tau.detach().cpu()
+                steps = torch.round(tau / dt)
+                if not bool((steps == steps.flatten()[0]).all()):
                     raise NotImplementedError("sub-trajectory length must be the same for all envs of a batch")
                 tau0 = float(tau.flatten()[0])
             else:
@@ -124,9 +126,24 @@ class MPInterface:
     def table_key(self):
         """identifies the shared tables of the current plan (handles are cached under it)"""
         pg = self.phase_gn
-        if not pg.uniform():
-            raise NotImplementedError("per-env tau/delay is not supported on the table-driven kernels")
         return (self.n_steps, round(self.init_time / self.dt), pg.scalar_tau(), pg.scalar_delay())
+
+    def _phase_basis(self) -> "_lib.FgPhaseBasis":
+        """constants of the phase / basis generators for the per-env-phase kernel (fg_phase_basis)"""
+        bg, pg = self.basis_gn, self.phase_gn
+        if type(bg).__name__ == "ProDMPBasisGenerator" or self.mp_kind not in (_lib.MP_PROMP, _lib.MP_DMP):
+            raise NotImplementedError("per-env tau / delay is available for ProMP and DMP (ProDMP's pre-integrated bases "
+                                      "depend on tau); use one tau per batch")
+        pb = _lib.FgPhaseBasis()
+        pb.struct_size = C.sizeof(_lib.FgPhaseBasis)
+        pb.phase_kind = 1 if pg.kind == "exp" else 0
+        pb.alpha_phase = float(getattr(pg, "alpha_phase", 0.0))
+        pb.n_basis_total, pb.first_learnable = bg.total_num_basis, bg.first_learnable
+        if bg.total_num_basis > 16:
+            raise NotImplementedError("per-env phase: at most 16 basis functions")
+        for k in range(bg.total_num_basis):
+            pb.centers[k], pb.bandwidth[k] = float(bg.centers_p[k]), float(bg.bandwidth[k])
+        return pb
 
     # ---- stand-alone trajectory generation on the GPU (fg_trajgen) ------------------------------
     def _trajgen_handle(self):
@@ -176,9 +193,18 @@ class MPInterface:
             pos, vel = out
             assert pos.shape == (B, T, N) and vel.shape == (B, T, N) and pos.is_contiguous() and vel.is_contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(_lib.lib.fg_trajgen(self._trajgen_handle(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
-                                       bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(), B,
-                                       C.c_void_p(stream)))
+        if self.phase_gn.uniform():
+            _lib.check(_lib.lib.fg_trajgen(self._trajgen_handle(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
+                                           bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(), B,
+                                           C.c_void_p(stream)))
+        else:       # per-env tau / delay: basis evaluated in the kernel (fg_trajgen_phase)
+            pb = self._phase_basis()
+            tau, delay = self.phase_gn.per_env(B, self.device)
+            times = torch.as_tensor(self.times32(), device=self.device)
+            _lib.check(_lib.lib.fg_trajgen_phase(self._trajgen_handle(), C.byref(pb), times.data_ptr(), tau.data_ptr(),
+                                                 delay.data_ptr(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
+                                                 bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(),
+                                                 B, C.c_void_p(stream)))
         return (pos, vel) if batched else (pos[0], vel[0])
 
     # ---- trajectory covariance of the probabilistic MPs (fg_traj_cov; mp_pytorch: set_mp_params_variances,
@@ -252,8 +278,9 @@ class ProMP(MPInterface):
         b = self.basis_gn.learnable_basis32(t32)
         tab_a = (b * np.float32(self.weights_scale)).astype(np.float32)
         tab_b = np.diff(t32).astype(np.float32)
+        # (weights_scale is folded into tab_a; the per-env-phase kernel, which has no table, takes it from the config)
         return MPTables(mp_kind=self.mp_kind, n_basis=self.basis_gn.num_basis, n_steps=len(t32), tab_a=tab_a, tab_b=tab_b,
-                        tau=self.phase_gn.scalar_tau())
+                        tau=self.phase_gn.scalar_tau(), weights_scale=float(self.weights_scale))
 
 
 class DMP(MPInterface):

@@ -41,21 +41,22 @@ class PhaseGenerator:
         return int(self.learn_tau) + int(self.learn_delay)
 
     def set_params(self, params: torch.Tensor) -> torch.Tensor:
-        """Consumes [tau][delay] from the front of params[..., P]; returns the remaining columns."""
+        """Consumes [tau][delay] from the front of params[..., P]; returns the remaining columns.  For a batch the values
+        stay on the params' device as [B] float32 tensors (per-env phase, no host synchronisation); the caller has
+        already clipped them to tau_bound / delay_bound (black_box_wrapper.py:104-105)."""
         i = 0
-        if self.learn_tau:
+        for flag, name in ((self.learn_tau, "tau"), (self.learn_delay, "delay")):
+            if not flag:
+                continue
             if not self.is_finalized:
-                tau = params[..., i].detach().to("cpu", torch.float32)
-                if not bool((tau > 0).all()):
-                    raise AssertionError("tau must be positive")
-                self.tau = tau
-            i += 1
-        if self.learn_delay:
-            if not self.is_finalized:
-                delay = params[..., i].detach().to("cpu", torch.float32)
-                if not bool((delay >= 0).all()):
-                    raise AssertionError("delay must be non-negative")
-                self.delay = delay
+                v = params[..., i].detach().to(torch.float32)
+                if v.numel() <= 1:          # single env: a host scalar, shared tables
+                    v = v.reshape(()).cpu()
+                    if name == "tau" and not float(v) > 0:
+                        raise AssertionError("tau must be positive")
+                    if name == "delay" and not float(v) >= 0:
+                        raise AssertionError("delay must be non-negative")
+                setattr(self, name, v)
             i += 1
         self.finalize()
         return params[..., i:]
@@ -70,16 +71,23 @@ class PhaseGenerator:
 
     # -- numerics (float32 linear phase exactly as the library's elementwise torch ops) ---------
     def uniform(self) -> bool:
-        """True when tau and delay are the same for every env of the batch (shared tables)."""
-        def same(x):
-            return x.dim() == 0 or x.numel() <= 1 or bool((x == x.reshape(-1)[0]).all())
-        return same(self.tau) and same(self.delay)
+        """True when tau and delay are scalars shared by every env of the batch (shared tables); per-env values ([B]
+        tensors) are handled by the per-env-phase kernels without looking at them on the host."""
+        return self.tau.dim() == 0 and self.delay.dim() == 0
 
     def scalar_tau(self) -> float:
-        return float(self.tau.reshape(-1)[0])
+        """tau for the shared tables; with a per-env phase the construction-time value (tables are nominal then)"""
+        return float(self.tau) if self.tau.dim() == 0 else self._tau0
 
     def scalar_delay(self) -> float:
-        return float(self.delay.reshape(-1)[0])
+        return float(self.delay) if self.delay.dim() == 0 else self._delay0
+
+    def per_env(self, num_envs: int, device):
+        """(tau [B], delay [B]) float32 on the device"""
+        def expand(x):
+            x = x.to(device, torch.float32)
+            return x.expand(num_envs).contiguous() if x.dim() == 0 else x.contiguous()
+        return expand(self.tau), expand(self.delay)
 
     def linear_phase32(self, times32: np.ndarray, clip_hi: bool = True) -> np.ndarray:
         tau, delay = np.float32(self.scalar_tau()), np.float32(self.scalar_delay())

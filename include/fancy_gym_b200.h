@@ -218,6 +218,28 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
 fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_pos, const float* bc_vel,
                      float* pos_out, float* vel_out, int64_t B, void* stream);
 
+/* Phase / basis generator constants for trajectory generation with a PER-ENV phase (learned tau / delay,
+ * phase_generator_kwargs learn_tau / learn_delay; mp_pytorch phase_gn + basis_gn).  RBFs: exp(-(phase - center)^2 * bandwidth / 2),
+ * normalised over all n_basis_total functions; only [first_learnable, first_learnable + n_basis) carry weights (zero padding). */
+typedef struct fg_phase_basis {
+  uint32_t struct_size;
+  int32_t phase_kind;          /* 0 = linear, 1 = exponential decay exp(-alpha_phase * z) */
+  double alpha_phase;
+  int32_t n_basis_total;       /* <= 16 */
+  int32_t first_learnable;
+  double centers[16];          /* in phase space */
+  double bandwidth[16];
+} fg_phase_basis;
+
+/*
+ * fg_trajgen with per-env tau / delay (ProMP and DMP): the basis is evaluated in the kernel instead of read from the
+ * handle's shared tables.  times [T] float32 time grid and tau / delay [B] float32 are DEVICE pointers; params holds the
+ * MP parameters only (tau / delay already stripped).  The fused rollout consumes pos_out / vel_out through a FG_MP_TRAJ handle.
+ */
+fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const float* times, const float* tau,
+                           const float* delay, const float* params, const float* bc_pos, const float* bc_vel,
+                           float* pos_out, float* vel_out, int64_t B, void* stream);
+
 /*
  * Trajectory covariance of the probabilistic MPs — replaces mp_pytorch's ProMP / ProDMP get_traj_pos_cov() /
  * get_traj_pos_std() behind the traj_gen object (no call site inside fancy_gym):

@@ -281,3 +281,68 @@ def test_blackbox_reset_fast_path_matches_wrapper_chain():
         b, _ = slow.reset(seed=5)
         assert a.shape == b.shape == (B, fast.observation_space.shape[0])
         assert torch.allclose(a, b, rtol=0, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------
+# per-env learned tau / delay: basis evaluated in the kernel, rollout from the HBM trajectory
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_id,phase", [("fancy_ProMP/HoleReacher-v0", dict(learn_tau=True, learn_delay=True)),
+                                          ("fancy_ProMP/HoleReacher-v0", dict(learn_delay=True)),
+                                          ("fancy_DMP/ViaPointReacher-v0", dict(learn_tau=True)),
+                                          ("fancy_DMP/HoleReacher-v0", dict(learn_tau=True, learn_delay=True)),
+                                          ("fancy_ProMP/SimpleReacher-v0", dict(learn_tau=True))],
+                         ids=["promp-tau-delay", "promp-delay", "dmp-tau", "dmp-tau-delay", "promp-pd-tau"])
+def test_per_env_tau_delay_matches_oracle(env_id, phase):
+    fancy_gym = _fg()
+    B = 300 + 7
+    mp_type = "promp" if "ProMP" in env_id else "dmp"
+    base_phase = dict(RESOLVED_PHASE(env_id), **phase)
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override={"phase_generator_kwargs": base_phase})
+    env.reset(seed=50)
+    rng = np.random.default_rng(4)
+    n_extra = int(phase.get("learn_tau", False)) + int(phase.get("learn_delay", False))
+    params = (0.4 * rng.standard_normal((B, n_params_of(env_id) + n_extra))).astype(np.float32)
+    i = 0
+    if phase.get("learn_tau"):
+        params[:, i] = rng.uniform(0.3, 2.5, B)          # partly outside tau_bound = [0.02, 2.0]: clipped like the reference
+        i += 1
+    if phase.get("learn_delay"):
+        params[:, i] = rng.uniform(0.0, 0.6, B)
+    assert env.action_space.shape[0] == params.shape[1]
+
+    orc = make_oracle(env_id, mode="mirror", mp_overrides={"phase": phase})
+    orc.reset(seeds=50 + np.arange(B))
+    o_pos, o_vel = orc.get_trajectory(params)
+    pos, vel = env.get_trajectory(torch.as_tensor(params, device="cuda:0"))
+    pos, vel = pos.cpu().numpy(), vel.cpu().numpy()
+    # same arithmetic as the shared-table path (float64 transcendental part rounded once): equal up to the last-bit
+    # differences of exp() between libm and CUDA
+    assert np.abs(pos - o_pos).max() <= 2e-6 * max(1.0, np.abs(o_pos).max())
+    vscale = max(1.0, np.abs(o_vel).max())
+    assert np.abs(vel - o_vel).max() <= 3e-5 * vscale
+    if phase.get("learn_tau") and phase.get("learn_delay") and mp_type == "promp":
+        # the linear phase saturates: constant trajectory after delay + tau, constant before the delay
+        tau = np.clip(params[:, 0], 0.02, 2.0)
+        delay = np.clip(params[:, 1], 0, 1.98)
+        late = (delay + tau) < 1.8
+        assert late.any()
+        for b in np.nonzero(late)[0][:20]:
+            n_end = int(np.ceil((delay[b] + tau[b]) / 0.01)) + 1
+            assert np.all(pos[b, n_end:] == pos[b, -1])
+
+    orc.reset(seeds=50 + np.arange(B))
+    o_obs, o_ret, o_te, o_tr, o_info = orc.step(params)
+    obs, ret, te, tr, info = env.step(torch.as_tensor(params, device="cuda:0"))
+    obs, ret, te, tr = obs.cpu().numpy(), ret.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
+    length = info["trajectory_length"].cpu().numpy()
+    tie = o_info["min_margin"] < TIE_EPS
+    agree = (length == o_info["trajectory_length"]) & (te == o_te) & (tr == o_tr)
+    assert (agree | tie).all() and (~agree).sum() <= 3
+    fin = agree & np.isfinite(o_ret)
+    assert not fin.any() or rel_err(ret[fin], o_ret[fin]).max() < 1e-5
+    assert (np.abs(obs[agree] - o_obs[agree]) <= 2e-5 * np.maximum(1.0, np.abs(o_obs[agree]))).all()
+
+
+def RESOLVED_PHASE(env_id):
+    from oracle.blackbox import RESOLVED
+    return dict(RESOLVED[env_id]["phase"])
