@@ -10,7 +10,10 @@
 
 namespace fg {
 
-constexpr int kRolloutThreads = 128;
+#ifndef FG_ROLLOUT_THREADS
+#define FG_ROLLOUT_THREADS 128
+#endif
+constexpr int kRolloutThreads = FG_ROLLOUT_THREADS;
 
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 
@@ -31,8 +34,11 @@ __host__ __device__ inline size_t rollout_smem_floats(int T, int cols_a, int row
 //         weights live in REGISTERS and the (float4-padded) table rows are fetched with vector broadcast loads.
 // KC == 0: run-time K; weights stay in shared memory (k-major, thread-minor: conflict free).
 // DBG: the verbose>=2 variant that also writes the per-step actions / observations / rewards (black_box_wrapper.py:208-213).
+#ifndef FG_ROLLOUT_MINB
+#define FG_ROLLOUT_MINB 1
+#endif
 template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
-__global__ void __launch_bounds__(kRolloutThreads)
+__global__ void __launch_bounds__(kRolloutThreads, FG_ROLLOUT_MINB)
 k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
           const int seg_steps) {
   extern __shared__ __align__(16) float smem[];
