@@ -1,7 +1,7 @@
 # Builds the C-ABI shared library (sm_100a) and the oracle's native pieces.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -Ifancy_gym_b200/csrc --expt-relaxed-constexpr
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xfatbin=-compress-all -Xcompiler -fPIC -Iinclude -Ifancy_gym_b200/csrc --expt-relaxed-constexpr
 SRC_DIR   := fancy_gym_b200/csrc
 BUILD_DIR := build/obj
 LIB       := fancy_gym_b200/lib/libfancygym_b200.so

@@ -56,9 +56,13 @@ cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t s
 #define FG_DECL_ENV_LAUNCH(name)                                                                              \
   cudaError_t name(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,        \
                    cudaStream_t stream, int max_smem_optin, const char** why)
-FG_DECL_ENV_LAUNCH(launch_rollout_hole);
-FG_DECL_ENV_LAUNCH(launch_rollout_viapoint);
-FG_DECL_ENV_LAUNCH(launch_rollout_simple);
+#define FG_DECL_ENV_DOFS(env)                                                                              \
+  FG_DECL_ENV_LAUNCH(launch_rollout_##env##_2); FG_DECL_ENV_LAUNCH(launch_rollout_##env##_3);                 \
+  FG_DECL_ENV_LAUNCH(launch_rollout_##env##_4); FG_DECL_ENV_LAUNCH(launch_rollout_##env##_5);                 \
+  FG_DECL_ENV_LAUNCH(launch_rollout_##env##_6); FG_DECL_ENV_LAUNCH(launch_rollout_##env##_7);
+FG_DECL_ENV_DOFS(hole)
+FG_DECL_ENV_DOFS(viapoint)
+FG_DECL_ENV_DOFS(simple)
 FG_DECL_ENV_LAUNCH(launch_rollout_toy);
 
 }  // namespace fg

@@ -38,7 +38,8 @@ template <int ENV, int MP, bool MOTOR, int N>
 cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
                        int max_smem_optin, const char** why) {
   // num_basis = 5 is the registry default of every MP type (registry.py:76-125): register-resident weights
-  if constexpr (MP != FG_MP_TRAJ) {
+  // (instantiated for the registered link counts only — 5 links, SimpleReacher's 2 — to keep the library small)
+  if constexpr (MP != FG_MP_TRAJ && (N == 5 || N == 2)) {
     if (c.K == 5) return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why);
   }
   return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why);

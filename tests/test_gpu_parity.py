@@ -346,3 +346,72 @@ def test_per_env_tau_delay_matches_oracle(env_id, phase):
 def RESOLVED_PHASE(env_id):
     from oracle.blackbox import RESOLVED
     return dict(RESOLVED[env_id]["phase"])
+
+
+# --------------------------------------------------------------------------------------------
+# generic kernel paths: run-time basis count (not the registry default 5), other trajectory lengths, other link counts
+# --------------------------------------------------------------------------------------------
+GENERIC_CASES = [("fancy_ProMP/HoleReacher-v0", {"basis": dict(num_basis=7)}, {}),
+                 ("fancy_ProMP/HoleReacher-v0", {"basis": dict(num_basis=3, num_basis_zero_start=2)}, {}),
+                 ("fancy_DMP/ViaPointReacher-v0", {"basis": dict(num_basis=8)}, {}),
+                 ("fancy_ProDMP/SimpleReacher-v0", {"basis": dict(num_basis=4)}, {}),
+                 ("fancy_ProDMP/HoleReacher-v0", {"basis": dict(num_basis=6), "phase": dict(tau=2.0)}, {}),
+                 ("fancy_ProMP/SimpleReacher-v0", {"basis": dict(num_basis=6)}, dict(n_links=3))]
+
+
+@pytest.mark.parametrize("env_id,over,env_over", GENERIC_CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(GENERIC_CASES)])
+def test_generic_kernel_paths_match_oracle(env_id, over, env_over):
+    fancy_gym = _fg()
+    B = 200 + 3
+    from oracle.blackbox import RESOLVED
+    names = {"basis": "basis_generator_kwargs", "phase": "phase_generator_kwargs"}
+    mp_over = {names[k]: dict(RESOLVED[env_id][k], **v) for k, v in over.items()}
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override=mp_over, **env_over)
+    env.reset(seed=9)
+    P = env.action_space.shape[0]
+    params = (0.5 * np.random.default_rng(2).standard_normal((B, P))).astype(np.float32)
+    orc = make_oracle(env_id, mode="mirror", mp_overrides=dict(over, env=env_over))
+    orc.reset(seeds=9 + np.arange(B))
+    o_pos, o_vel = orc.get_trajectory(params)
+    pos, vel = env.get_trajectory(torch.as_tensor(params, device="cuda:0"))
+    assert np.array_equal(pos.cpu().numpy(), o_pos) and np.array_equal(vel.cpu().numpy(), o_vel)     # mirror mode: bit-exact
+    o_obs, o_ret, o_te, o_tr, o_info = orc.step(params)
+    obs, ret, te, tr, info = env.step(torch.as_tensor(params, device="cuda:0"))
+    length = info["trajectory_length"].cpu().numpy()
+    tie = o_info["min_margin"] < TIE_EPS
+    agree = (length == o_info["trajectory_length"]) & (te.cpu().numpy() == o_te) & (tr.cpu().numpy() == o_tr)
+    assert (agree | tie).all()
+    fin = agree & np.isfinite(o_ret)
+    assert not fin.any() or rel_err(ret.cpu().numpy()[fin], o_ret[fin]).max() < 1e-5
+    assert (np.abs(obs.cpu().numpy()[agree] - o_obs[agree]) <= 1e-5 * np.maximum(1.0, np.abs(o_obs[agree]))).all()
+
+
+def test_trajgen_ragged_lengths_and_long_trajectories():
+    """T not a multiple of 4 (ragged last quad) and T * dof beyond the staging buffer (chunked path)"""
+    fancy_gym = _fg()
+    from tests.toy import ToyWrapper, register_toy
+    register_toy(fancy_gym)
+    for mp_type, basis in (("promp", "rbf"), ("prodmp", "prodmp")):
+        for dof in (1, 5):
+            env = fancy_gym.make_bb("toy-v0", [ToyWrapper], {}, {"trajectory_generator_type": mp_type, "action_dim": dof},
+                                    {"controller_type": "motor"}, {"phase_generator_type": "exp"},
+                                    {"basis_generator_type": basis, "num_basis": 5}, device="cuda:0", num_envs=33, n_links=dof)
+            tg = env.traj_gen
+            for duration in (0.98, 1.0, 4.22, 30.0 if mp_type == "promp" else 5.5):   # T = 49, 50, 211, 1500 (275: ProDMP pre-computes 6 tau)
+                tg.set_duration(duration, 0.02)
+                p = torch.randn(33, tg.num_params, device="cuda:0")
+                tg.set_params(p)
+                tg.set_initial_conditions(0.0, torch.ones(33, dof, device="cuda:0"), torch.zeros(33, dof, device="cuda:0"))
+                pos, vel = tg._run_trajgen()
+                T = int(round(duration / 0.02))
+                assert pos.shape == (33, T, dof) and bool(torch.isfinite(pos).all()) and bool(torch.isfinite(vel).all())
+                tb = tg.tables()
+                w = p.reshape(33, dof, -1).cpu().numpy().astype(np.float32)
+                if mp_type == "promp":      # pos = fma chain over the table row; vel = finite difference, last row duplicated
+                    ref = np.zeros((33, T, dof), np.float32)
+                    for k in range(tb.tab_a.shape[1]):
+                        ref = (np.float32(tb.tab_a[None, :, None, k]) * w[:, None, :, k]).astype(np.float64) + ref
+                        ref = ref.astype(np.float32)
+                    assert np.abs(pos.cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+                    v = vel.cpu().numpy()
+                    assert np.array_equal(v[:, -1], v[:, -2])
