@@ -87,12 +87,12 @@ class BlackBoxWrapper(Wrapper):
         self._obs_index_np = np.asarray(self._obs_index())
         # (return | length | flags) of a step live in ONE contiguous byte block: the multi-GPU exchange is a single
         # all-gather of that block, with no packing kernels (fancy_gym_b200/dist).
-        from ..dist import result_block_bytes, result_block_views
+        from ..dist import result_block_bytes, result_block_flag_bytes, result_block_views
         self._out_sets = []
         for _ in range(2):
             block = torch.zeros(result_block_bytes(B), dtype=torch.uint8, device=dev)
             r, ln, fl = result_block_views(block, B)
-            self._out_sets.append(dict(block=block, ret=r, len=ln, flags=fl,
+            self._out_sets.append(dict(block=block, ret=r, len=ln, flags=fl, flag_bytes=result_block_flag_bytes(block, B),
                                        info=torch.zeros(B, 4, dtype=torch.float64, device=dev),
                                        obs=torch.zeros(B, len(self._obs_index_np), dtype=torch.float32, device=dev)))
         self._out_i = 0
@@ -124,14 +124,20 @@ class BlackBoxWrapper(Wrapper):
         o = self._out_sets[self._out_i]
         self._ret, self._len, self._flags, self._info, self._obs = o["ret"], o["len"], o["flags"], o["info"], o["obs"]
         self._result_block = o["block"]
+        self._flag_bytes = o["flag_bytes"]        # bool views: terminated, truncated, is_success, is_collided
 
     def _flip_outputs(self):
-        """next result set; the "unbounded" HoleReacher reward keeps per-episode state in info[:, 2:4] (fg_rollout_io.info)"""
-        prev = self._info
+        """next result set.  Envs whose episode ended in an earlier call are skipped by the kernel, so while several plans
+        share one episode (replanning / sub-trajectories) their last observation and infos are carried over; the "unbounded"
+        HoleReacher reward keeps per-episode state in info[:, 2:4] (fg_rollout_io.info)."""
+        prev_info, prev_obs = self._info, self._obs
         self._out_i ^= 1
         self._bind_outputs()
-        if getattr(self._base, "rew_fct", None) == "unbounded":
-            self._info[:, 2:4] = prev[:, 2:4]
+        if self.do_replanning or self.learn_sub_trajectories:
+            self._obs.copy_(prev_obs)
+            self._info.copy_(prev_info)
+        elif getattr(self._base, "rew_fct", None) == "unbounded":
+            self._info[:, 2:4] = prev_info[:, 2:4]
 
     # ---- spaces (black_box_wrapper.py:122-148) --------------------------------------------------
     def _get_traj_gen_action_space(self):
@@ -308,6 +314,7 @@ class BlackBoxWrapper(Wrapper):
         io.write_cond = (2 if replan_break else 1) if self.condition_on_desired else 0
         io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
         io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
+        io.flag_bytes = self._flag_bytes[0].data_ptr()
         if dbg is not None:
             io.dbg_rewards = dbg["rewards"].data_ptr()
             if "actions" in dbg:
@@ -340,16 +347,13 @@ class BlackBoxWrapper(Wrapper):
 
         self.current_traj_steps += seg     # live envs all advance by `seg`; finished envs are frozen
         length = self._len
-        flags = self._flags
-        terminated = (flags & _lib.FLAG_TERMINATED) != 0
-        truncated = (flags & _lib.FLAG_TRUNCATED) != 0
+        terminated, truncated, success, collided = self._flag_bytes      # written by the kernel: no unpacking ops
         ret = self._ret
         if self.reward_aggregation is np.mean:
             ret = ret / length.clamp(min=1)
         infos: Dict[str, Any] = {}
         if base.env_kind in (_lib.ENV_HOLE_REACHER, _lib.ENV_VIAPOINT_REACHER):
-            infos["is_success"] = (flags & _lib.FLAG_SUCCESS) != 0
-            infos["is_collided"] = (flags & _lib.FLAG_COLLIDED) != 0
+            infos["is_success"], infos["is_collided"] = success, collided
             infos["end_effector"] = self._info[:, 0:2]
             if getattr(base, "rew_fct", None) == "unbounded":        # hr_unbounded_reward.py:53-56
                 infos["joints"] = base.q.clone()
@@ -415,13 +419,11 @@ class BlackBoxWrapper(Wrapper):
         base = self._base
         if self._fast_reset and not {k for k in (options or {}) if k != "as_numpy"}:
             # one kernel: numpy-exact context sampling + state reset + context observation (fg_reset)
-            self._flip_outputs()
-            obs, info = base.device_reset(seed, obs_index=self._obs_index_np, time_aware=self._time_aware(), out=self._obs), {}
+            obs, info = base.device_reset(seed, obs_index=self._obs_index_np, time_aware=self._time_aware()), {}
         else:
             obs, info = self.env.reset(seed=seed, options={k: v for k, v in (options or {}).items() if k != "as_numpy"} or None)
-            self._flip_outputs()
-            self._obs.copy_(self.observation(obs))
-            obs = self._obs
+            obs = self.observation(obs).contiguous()
+        self._obs.copy_(obs)        # what a frozen env would report; the returned tensor is the caller's own
         as_numpy = (options or {}).get("as_numpy", self.num_envs == 1)
         if as_numpy:
             obs = obs.cpu().numpy()

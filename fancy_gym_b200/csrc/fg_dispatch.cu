@@ -58,6 +58,29 @@ cudaError_t launch_closed(const DevCfg& c, const float* params, const float* bc_
   return cudaGetLastError();
 }
 
+template <int N>
+cudaError_t launch_dmp(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel, float* pos_out,
+                       float* vel_out, long long B, cudaStream_t stream, int max_smem_optin, int sm_count, const char** why) {
+  constexpr int G = 32 / N;
+  const int RA = (c.K + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)kDmpWarps * G * 2 * kDmpChunk * N + (size_t)c.T * RA + c.T);
+  if (smem > (size_t)max_smem_optin) {
+    *why = "tables exceed the shared memory of one SM";
+    return cudaSuccess;
+  }
+  auto kern = k_trajgen_dmp<N>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  // hardware-scheduled blocks of consecutive envs (see launch_closed): a multiple of the envs one block handles per pass
+  int epb = kDmpWarps * G * 4;
+  while (epb > kDmpWarps * G && (B + epb - 1) / epb < (long long)sm_count * 8) epb -= kDmpWarps * G;
+  const unsigned blocks = (unsigned)((B + epb - 1) / epb);
+  kern<<<blocks, kDmpThreads, smem, stream>>>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, epb);
+  return cudaGetLastError();
+}
+
 template <int MP, int N>
 cudaError_t launch_closed_k(const DevCfg& c, const float* params, const float* bc_pos, const float* bc_vel,
                             float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
@@ -91,19 +114,18 @@ cudaError_t launch_trajgen(const DevCfg& c, int mp_kind, const float* params, co
   if (mp_kind == FG_MP_PRODMP)
     return launch_closed_n<FG_MP_PRODMP>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
   if (mp_kind == FG_MP_DMP) {
-    const size_t smem = sizeof(float) * ((size_t)c.T * c.K + (size_t)c.T);
-    if (smem > (size_t)max_smem_optin) {
-      *why = "tables exceed the shared memory of one SM";
+    if (c.K > 16) {
+      *why = "DMP trajectory kernel: at most 16 basis functions";
       return cudaSuccess;
     }
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(k_trajgen_dmp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
+#define FG_DMP(n) \
+  case n: return launch_dmp<n>(c, params, bc_pos, bc_vel, pos_out, vel_out, B, stream, max_smem_optin, sm_count, why);
+    switch (c.n_dof) {
+      FG_DMP(1) FG_DMP(2) FG_DMP(3) FG_DMP(4) FG_DMP(5) FG_DMP(6) FG_DMP(7) FG_DMP(8)
     }
-    const long long el = B * c.n_dof;
-    k_trajgen_dmp<<<(unsigned)((el + kTrajThreads - 1) / kTrajThreads), kTrajThreads, smem, stream>>>(
-        c, params, bc_pos, bc_vel, pos_out, vel_out, B);
-    return cudaGetLastError();
+#undef FG_DMP
+    *why = "n_dof out of range";
+    return cudaSuccess;
   }
   *why = "no trajectory generator for this mp_kind";
   return cudaSuccess;

@@ -94,6 +94,8 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     io.ret[b] = 0.0;
     io.length[b] = 0;
     io.flags[b] = 0;
+    if (io.flag_bytes)
+      for (int i = 0; i < 4; ++i) io.flag_bytes[i * B + b] = 0;
     return;
   }
 
@@ -542,6 +544,12 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   io.length[b] = len;
   io.flags[b] = (terminated ? FG_FLAG_TERMINATED : 0u) | (truncated ? FG_FLAG_TRUNCATED : 0u) |
                 (success ? FG_FLAG_SUCCESS : 0u) | (collided ? FG_FLAG_COLLIDED : 0u);
+  if (io.flag_bytes) {
+    io.flag_bytes[b] = terminated;
+    io.flag_bytes[B + b] = truncated;
+    io.flag_bytes[2 * B + b] = success;
+    io.flag_bytes[3 * B + b] = collided;
+  }
 
   // observation after the last executed step
   float obs[FG_MAX_OBS];

@@ -234,47 +234,114 @@ k_trajgen_closed(const __grid_constant__ DevCfg c, const float* __restrict__ par
   if (pending) bulk_wait_read0();       // the stage must stay valid until the TMA engine has read it
 }
 
-// DMP: serial semi-implicit Euler per (env, dof); one thread per (env, dof) pair.
-__global__ void __launch_bounds__(kTrajThreads)
+// DMP: the Euler recurrence is serial in time, so a lane owns one (env, dof) pair and a warp G = 32 / N envs.  The lanes
+// write their position / scaled velocity into a per-warp staging buffer, CH time points at a time, and every env's
+// [CH, N] blocks then leave the SM as TMA bulk stores (instead of 20-byte pieces scattered over G different lines per
+// store instruction); the recurrence of the next chunk overlaps the drain.
+constexpr int kDmpThreads = 128;
+constexpr int kDmpWarps = kDmpThreads / 32;
+constexpr int kDmpChunk = 40;            // time points staged at a time (a multiple of 4: 16-byte sized bulk copies)
+
+template <int N>
+__global__ void __launch_bounds__(kDmpThreads)
 k_trajgen_dmp(const __grid_constant__ DevCfg c, const float* __restrict__ params, const float* __restrict__ bc_pos,
               const float* __restrict__ bc_vel, float* __restrict__ pos_out, float* __restrict__ vel_out,
-              const long long B) {
-  extern __shared__ float smem[];
-  const int T = c.T, K = c.K, N = c.n_dof;
-  float* tabA = smem;            // [T, K]
-  float* tabB = tabA + T * K;    // [T-1]
-  for (int i = threadIdx.x; i < T * K; i += kTrajThreads) tabA[i] = c.tab_a[i];
-  for (int i = threadIdx.x; i < T - 1; i += kTrajThreads) tabB[i] = c.tab_b[i];
+              const long long B, const int envs_per_block) {
+  extern __shared__ __align__(128) float smem[];
+  constexpr int G = 32 / N;                                  // envs per warp
+  constexpr int SE = 2 * kDmpChunk * N;                      // staging floats per env (pos | vel)
+  const int T = c.T, K = c.K;
+  const int RA = (K + 3) & ~3;
+  float* stage = smem;                                       // [warps][G][2][kDmpChunk * N]
+  float* tabA = stage + kDmpWarps * G * SE;                  // [T, RA]
+  float* tabB = tabA + T * RA;                               // [T]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < T * RA; i += kDmpThreads) {
+    const int r = i / RA, col = i - r * RA;
+    tabA[i] = (col < K) ? c.tab_a[r * K + col] : 0.f;
+  }
+  for (int i = tid; i < T - 1; i += kDmpThreads) tabB[i] = c.tab_b[i];
   __syncthreads();
-  const long long e = (long long)blockIdx.x * kTrajThreads + threadIdx.x;   // (b, d) flat
-  if (e >= B * N) return;
-  const long long b = e / N;
-  const int d = (int)(e % N);
-  const float* pr = params + b * N * (K + 1) + d * (K + 1);
-  float w[16];
-  const int Kc = min(K, 16);
+  const int e = lane / N, d = lane - e * N;
+  const bool lane_used = lane < G * N;
+  const float r_tau = __frcp_rn(c.tau);
+  const bool bulk = ((T * N) % 4 == 0);
+  const long long b_end = min(B, ((long long)blockIdx.x + 1) * envs_per_block);
+  float* st = stage + (warp * G + e) * SE;
+  bool pending = false;
+  for (long long b0 = (long long)blockIdx.x * envs_per_block + warp * G; b0 < b_end; b0 += kDmpWarps * G) {
+    const long long b = b0 + e;
+    const bool valid = lane_used && b < b_end;
+    float w[16];
+    float g = 0.f, y = 0.f, yd = 0.f;
+    if (valid) {
+      const float* pr = params + (b * N + d) * (K + 1);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) w[k] = (k < Kc) ? __fmul_rn(pr[k], c.wscale) : 0.f;
-  const float g = __fmul_rn(pr[K], c.gscale);
-  float y = bc_pos[e], yd = __fmul_rn(bc_vel[e], c.tau);
-  for (int t = 0; t < T; ++t) {
-    pos_out[(b * T + t) * N + d] = y;
-    vel_out[(b * T + t) * N + d] = __fdiv_rn(yd, c.tau);
-    if (t < T - 1) {
-      const float* row = tabA + t * K;
-      float f = 0.f;
+      for (int k = 0; k < 16; ++k) w[k] = (k < K) ? __fmul_rn(pr[k], c.wscale) : 0.f;
+      g = __fmul_rn(pr[K], c.gscale);
+      y = bc_pos[b * N + d];
+      yd = __fmul_rn(bc_vel[b * N + d], c.tau);
+    }
+    for (int c0 = 0; c0 < T; c0 += kDmpChunk) {
+      const int rows = min(kDmpChunk, T - c0);
+      if (pending) {
+        bulk_wait_read0();
+        pending = false;
+      }
+      __syncwarp();
+      if (valid) {
+        for (int r = 0; r < rows; ++r) {
+          const int t = c0 + r;
+          st[r * N + d] = y;
+          st[kDmpChunk * N + r * N + d] = div_by(yd, c.tau, r_tau);
+          if (t < T - 1) {
+            const float* row = tabA + t * RA;
+            float f = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k < Kc) f = fmaf(row[k], w[k], f);
-      for (int k = Kc; k < K; ++k) f = fmaf(row[k], __fmul_rn(pr[k], c.wscale), f);
-      float a = __fmul_rn(c.beta, __fsub_rn(g, y));
-      a = __fmul_rn(c.alpha, __fsub_rn(a, yd));
-      a = __fadd_rn(a, f);
-      const float h = tabB[t];
-      yd = __fadd_rn(yd, __fmul_rn(h, a));
-      y = __fadd_rn(y, __fmul_rn(h, yd));
+            for (int k4 = 0; k4 < 4; ++k4)
+              if (4 * k4 < K) {
+                const float4 x = reinterpret_cast<const float4*>(row)[k4];
+                f = fmaf(x.x, w[4 * k4], f);
+                if (4 * k4 + 1 < K) f = fmaf(x.y, w[4 * k4 + 1], f);
+                if (4 * k4 + 2 < K) f = fmaf(x.z, w[4 * k4 + 2], f);
+                if (4 * k4 + 3 < K) f = fmaf(x.w, w[4 * k4 + 3], f);
+              }
+            float a = __fmul_rn(c.beta, __fsub_rn(g, y));
+            a = __fmul_rn(c.alpha, __fsub_rn(a, yd));
+            a = __fadd_rn(a, f);
+            const float h = tabB[t];
+            yd = __fadd_rn(yd, __fmul_rn(h, a));
+            y = __fadd_rn(y, __fmul_rn(h, yd));
+          }
+        }
+      }
+      float* gp = pos_out + (b * T + c0) * N;
+      float* gv = vel_out + (b * T + c0) * N;
+      if (bulk) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (valid && d == 0) {            // one lane per env issues that env's two bulk stores
+          bulk_store_s2g(gp, st, (unsigned)(rows * N * sizeof(float)));
+          bulk_store_s2g(gv, st + kDmpChunk * N, (unsigned)(rows * N * sizeof(float)));
+          bulk_commit();
+          pending = true;
+        }
+      } else {
+        __syncwarp();
+        for (int ee = 0; ee < G; ++ee) {
+          const long long be = b0 + ee;
+          if (be >= b_end) break;
+          const float* se = stage + (warp * G + ee) * SE;
+          for (int i = lane; i < rows * N; i += 32) {
+            pos_out[(be * T + c0) * N + i] = se[i];
+            vel_out[(be * T + c0) * N + i] = se[kDmpChunk * N + i];
+          }
+        }
+        __syncwarp();
+      }
     }
   }
+  if (pending) bulk_wait_read0();
 }
 
 }  // namespace fg

@@ -81,8 +81,9 @@ def gather_episode_results(ret, length, flags, total_envs: Optional[int] = None,
 # ---- zero-copy variant: the black-box wrapper keeps (return f64 | length i32 | flags u8) of a step in ONE contiguous
 # ---- byte block, so the per-step exchange is a single collective on that block with no packing kernels -------------
 def result_block_bytes(num_envs: int) -> int:
-    """bytes of one result block, padded to 16 so that typed views of the gathered blocks stay aligned"""
-    return (13 * num_envs + 15) // 16 * 16
+    """bytes of one result block (return f64 | length i32 | flags u8 | 4 unpacked flag bytes per env), padded to 16 so
+    that typed views of the gathered blocks stay aligned"""
+    return (17 * num_envs + 15) // 16 * 16
 
 
 def result_block_views(block: torch.Tensor, num_envs: int):
@@ -93,6 +94,14 @@ def result_block_views(block: torch.Tensor, num_envs: int):
     length = block[..., 8 * B:12 * B].view(torch.int32)
     flags = block[..., 12 * B:13 * B]
     return ret.reshape(*lead, B), length.reshape(*lead, B), flags.reshape(*lead, B)
+
+
+def result_block_flag_bytes(block: torch.Tensor, num_envs: int):
+    """bool views [.., B] of the unpacked flags: terminated, truncated, is_success, is_collided (written by the kernel)"""
+    B = num_envs
+    lead = block.shape[:-1]
+    fb = block[..., 13 * B:17 * B].view(torch.bool).reshape(*lead, 4, B)
+    return fb[..., 0, :], fb[..., 1, :], fb[..., 2, :], fb[..., 3, :]
 
 
 def all_gather_result_blocks(block: torch.Tensor, out: Optional[torch.Tensor] = None, group=None):

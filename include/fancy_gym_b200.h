@@ -152,6 +152,9 @@ typedef struct fg_rollout_io {
   double* dbg_actions;     /* [B, T, dof] infos['step_actions'] */
   float* dbg_obs;          /* [B, T, n_obs_full] infos['step_observations'] */
   double* dbg_rewards;     /* [B, T] infos['step_rewards'] */
+  /* optional unpacked copies of the flag bits, one byte (0 / 1) per env each, or NULL: what step() returns as
+   * terminated / truncated and infos['is_success'] / ['is_collided'] without any post-processing kernel */
+  uint8_t* flag_bytes;     /* [4, B]: rows terminated, truncated, success, collided */
 } fg_rollout_io;
 
 /* Episode reset of the classic_control reachers on the device (replaces the host-side samplers

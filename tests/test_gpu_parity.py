@@ -86,12 +86,16 @@ def test_rollout_matches_reference_goldens(case, golden_dir):
     obs0, _ = env.reset(seed=np.array(seeds), options={"as_numpy": True})
     assert np.allclose(obs0, g["obs0"], rtol=0, atol=1e-6)
     n_plans = g["params"].shape[1]
+    last_obs = {}
     for i in range(n_plans):
         live = i < g["n_calls"]
         if not live.any():
             break
         obs, ret, te, tr, info = env.step(g["params"][:, i])
+        for b in np.nonzero(~live)[0]:      # episode over in an earlier call: frozen, reports its last observation, 0 steps
+            assert info["trajectory_length"][b] == 0 and np.array_equal(obs[b], last_obs[b]), (fname, b, i)
         for b in np.nonzero(live)[0]:
+            last_obs[b] = np.array(obs[b])
             assert info["trajectory_length"][b] == g["length"][b, i], (fname, b, i)
             assert bool(te[b]) == bool(g["terminated"][b, i]) and bool(tr[b]) == bool(g["truncated"][b, i])
             r_ref = g["ret"][b, i]
@@ -415,3 +419,25 @@ def test_trajgen_ragged_lengths_and_long_trajectories():
                     assert np.abs(pos.cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
                     v = vel.cpu().numpy()
                     assert np.array_equal(v[:, -1], v[:, -2])
+
+
+def test_step_results_stay_valid_for_one_more_step():
+    """step() returns views of one of two alternating result sets: what step i returned must be untouched by step i+1
+    (and reset), and is recycled by step i+2."""
+    fancy_gym = _fg()
+    B = 1024
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device="cuda:0")
+    env.reset(seed=0)
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    p1, p2 = (0.5 * torch.randn(B, 25, generator=gen, device="cuda:0") for _ in range(2))
+    obs1, ret1, te1, tr1, info1 = env.step(p1)
+    snap = [x.clone() for x in (obs1, ret1, te1, tr1, info1["trajectory_length"], info1["is_collided"], info1["end_effector"])]
+    env.reset(seed=1)
+    obs2, ret2, te2, tr2, info2 = env.step(p2)
+    for a, b in zip(snap, (obs1, ret1, te1, tr1, info1["trajectory_length"], info1["is_collided"], info1["end_effector"])):
+        assert torch.equal(a, b)
+    assert not torch.equal(ret1, ret2)
+    assert ret1.data_ptr() != ret2.data_ptr()
+    # terminated / truncated are exactly the flag bits
+    assert torch.equal(te2, (env._flags & 1) != 0) and torch.equal(tr2, (env._flags & 2) != 0)
+    assert torch.equal(info2["is_success"], (env._flags & 4) != 0) and torch.equal(info2["is_collided"], (env._flags & 8) != 0)
