@@ -15,7 +15,8 @@ Prints ONE JSON line (see README / DESIGN.md "Measurement" for the keys):
   roofline         fused rollout kernel: algorithmic ops (4356 per HoleReacher/ProMP env step)
                    / measured kernel time, against the FP32 FFMA peak measured in the same run (fg_ffma_probe)
   roofline_trajgen trajectory-only kernel (fg_trajgen): algorithmic bytes (8 B per (t, dof)) / time vs measured HBM GB/s
-  cpu_baseline     the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1, bounded sample)
+  cpu_baseline     the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1, bounded sample):
+                   one env per process like the reference; the numpy-vectorised port is reported as an extra
 Multi-GPU (torchrun, one rank per GPU): the env batch is sharded, no data-path collective; per-step returns /
 lengths / flags are all-gathered over NCCL inside the timed region ("scaling": "weak").
 """
@@ -61,27 +62,49 @@ def _cpu_worker(args):
     return steps, n_batches * batch, time.perf_counter() - t0
 
 
-def cpu_reference_sample(n_batches, batch=CPU_BATCH, sigma=SIGMA):
-    """The oracle port of the reference path on ALL host cores: one worker process per core, each stepping `batch`
-    envs at a time through oracle/blackbox.py (BlackBoxWrapper.step loop, black_box_wrapper.py:150-217).
-    batch=1 has the reference's structure (one env per process, ~1.2k env-steps/s/core here; the reference's own files
-    reach ~2.1k/core); the default batch of 64 lets numpy vectorise over envs and is several times
-    FASTER per env than the reference itself, i.e. a deliberately strong CPU baseline."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(10_000_000 + 1000 * w, 1, min(batch, 4), sigma) for w in range(cores)])   # warm-up
+class CpuReference:
+    """The oracle port of the reference path on ALL host cores: one worker process per core (fork), each running whole
+    episodes through oracle/blackbox.py (the BlackBoxWrapper.step loop, black_box_wrapper.py:150-217, on oracle/reacher.py).
+
+    `batch=1` is the reference's own structure — one env per process, one Python-level env step at a time — and is what
+    `value` reports (kind "port"); calibration in the build container, which has /root/reference: the reference's own
+    BlackBoxWrapper + HoleReacherEnv files run 2.7k env-steps/s per core, this port 2.9k.  `batch=64` lets numpy vectorise over 64 envs per call: several times FASTER per env
+    than anything the reference can do; it is reported separately as `vectorised_port_value` ("not the reference")."""
+
+    def __init__(self, sigma=SIGMA):
+        import multiprocessing as mp
+        self.cores = os.cpu_count() or 1
+        self.sigma = sigma
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.pool.map(_cpu_worker, [(10_000_000 + 1000 * w, 1, 2, sigma) for w in range(self.cores)])      # warm-up / imports
+        self._next_seed = 0
+
+    def sample(self, n_batches, batch=1):
+        """every worker runs `n_batches` oracle calls of `batch` envs -> dict(env_steps, episodes, wall_s)"""
+        s0 = self._next_seed
+        self._next_seed += self.cores * n_batches * batch
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(100_000 * w, n_batches, batch, sigma) for w in range(cores)])
+        res = self.pool.map(_cpu_worker, [(s0 + w * n_batches * batch, n_batches, batch, self.sigma) for w in range(self.cores)])
         wall = time.perf_counter() - t0
-    steps = sum(r[0] for r in res)
-    eps = sum(r[1] for r in res)
-    return dict(value=steps / wall, unit="env-steps/s", cores=cores, kind="port",
-                episodes_per_s=eps / wall, wall_s=wall, env_steps=steps, episodes=eps,
-                sample=f"{eps} episodes ({steps} env steps) of {ENV_ID}, sigma={sigma}: {cores} worker processes x {n_batches} "
-                       f"batches of {batch} envs through oracle/blackbox.py ('shipped' float32 MP, collision tests twice per step "
-                       f"like the reference)")
+        return dict(env_steps=sum(r[0] for r in res), episodes=sum(r[1] for r in res), wall_s=wall)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def baseline(self, scalar_episodes_per_worker=8, vector_batches_per_worker=4):
+        """cpu_baseline object of the bench line: ~10-30 s of CPU work in total"""
+        sc = self.sample(scalar_episodes_per_worker, batch=1)
+        ve = self.sample(vector_batches_per_worker, batch=CPU_BATCH)
+        return dict(value=sc["env_steps"] / sc["wall_s"], unit="env-steps/s", cores=self.cores, kind="port",
+                    episodes_per_s=sc["episodes"] / sc["wall_s"], wall_s=sc["wall_s"], env_steps=sc["env_steps"],
+                    episodes=sc["episodes"],
+                    sample=f"{sc['episodes']} episodes ({sc['env_steps']} env steps) of {ENV_ID}, sigma={self.sigma}: {self.cores} worker "
+                           f"processes x {scalar_episodes_per_worker} episodes, one env per process stepped one env step at a time through "
+                           f"oracle/blackbox.py ('shipped' float32 MP, collision tests twice per step like the reference)",
+                    vectorised_port_value=ve["env_steps"] / ve["wall_s"],
+                    vectorised_port_note=f"NOT the reference: the same port with numpy vectorised over {CPU_BATCH} envs per call "
+                                         f"({ve['episodes']} episodes in {ve['wall_s']:.2f} s)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,28 +182,33 @@ def measured_peaks():
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's CPU path (oracle port: the reference is Python and /root/reference does not
-    travel to the GPU box) on all host cores; each step is a bounded sample of the workload.  Rank 0 only."""
+    """`--impl reference`: the reference's CPU path (oracle port: the reference is Python with uninstalled dependencies and
+    /root/reference does not travel to the GPU box) on all host cores.  One "step" is a bounded sample of the workload:
+    every worker process runs 2 episodes, one env at a time like the reference.  Rank 0 only."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cpu = CpuReference(args.sigma)
+    per_worker = 2
     for _ in range(min(args.warmup, 2)):
-        cpu_reference_sample(1)
+        cpu.sample(1)
     tot_steps = tot_eps = busy = 0.0
     for _ in range(args.steps):
-        r = cpu_reference_sample(1)
+        r = cpu.sample(per_worker)
         tot_steps += r["env_steps"]; tot_eps += r["episodes"]; busy += r["wall_s"]
     value = tot_steps / max(busy, 1e-9)
-    scalar = cpu_reference_sample(2, batch=1)
+    vec = cpu.sample(2, batch=CPU_BATCH)
+    cpu.close()
     line = dict(metric="env-steps/sec (fancy_ProMP/HoleReacher-v0 MP black-box rollout)", value=value, unit="env-steps/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * busy / max(args.steps, 1),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=f"{ENV_ID}, bounded CPU sample per step: {CPU_BATCH} envs x {cores} worker processes, sigma={SIGMA}"),
+                config=dict(workload=f"{ENV_ID}, bounded CPU sample per step: {per_worker} episodes x {cpu.cores} worker processes "
+                                     f"(one env per process), sigma={args.sigma}"),
                 episodes_per_s=tot_eps / max(busy, 1e-9),
-                cpu_baseline=dict(value=value, unit="env-steps/s", cores=cores, kind="port",
-                                  sample=f"{args.steps} steps x {CPU_BATCH * cores} episodes; numpy-vectorised oracle port, {CPU_BATCH} envs per "
-                                         f"worker call (stronger than the reference's one-env-per-process loop)",
-                                  scalar_port_value=scalar["value"]),
+                cpu_baseline=dict(value=value, unit="env-steps/s", cores=cpu.cores, kind="port",
+                                  sample=f"{args.steps} steps x {per_worker * cpu.cores} episodes; oracle port of the reference's loop, one env "
+                                         f"per process stepped one env step at a time",
+                                  vectorised_port_value=vec["env_steps"] / vec["wall_s"],
+                                  vectorised_port_note=f"NOT the reference: the same port vectorised over {CPU_BATCH} envs per call"),
                 e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -385,8 +413,9 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_sample(6, sigma=args.sigma)
-        cpu["scalar_port_value"] = cpu_reference_sample(2, batch=1, sigma=args.sigma)["value"]
+        ref = CpuReference(args.sigma)
+        cpu = ref.baseline()
+        ref.close()
 
     if rank == 0:
         line = dict(metric="env-steps/sec (fancy_ProMP/HoleReacher-v0 MP black-box rollout)", value=value, unit="env-steps/s",

@@ -130,6 +130,20 @@ def self_collision(q, J, allow_self_collision=False, margins=True):
         return np.zeros(B, bool), np.full(B, np.inf)
     limit = np.any(q > np.pi, axis=1) | np.any(q < -np.pi, axis=1)
     hit = np.zeros(B, bool)
+    if not margins and B == 1:
+        # one env, like the reference: plain Python float arithmetic on the joint coordinates (same IEEE operations as the
+        # array expressions below, without numpy's per-call overhead on 1-element arrays) — used by bench.py's CPU arm
+        P = J[0].tolist()
+
+        def ccw(a, b, c):
+            return (c[1] - a[1]) * (b[0] - a[0]) - (b[1] - a[1]) * (c[0] - a[0]) > CCW_EPS
+        h = False
+        for i in range(n):
+            for j in range(i + 2, n):
+                a, b_, c, d = P[i], P[i + 1], P[j], P[j + 1]
+                if ccw(a, c, d) != ccw(b_, c, d) and ccw(a, b_, c) != ccw(a, b_, d):
+                    h = True
+        return limit | np.array([h]), np.full(B, np.inf)
     if not margins:     # decision only, exactly the reference's arithmetic
         for i in range(n):
             for j in range(i + 2, n):
