@@ -39,6 +39,10 @@ SIGMA = 0.25
 CPU_BATCH = 64                   # envs per oracle call in the CPU baseline (numpy-vectorised port)
 OPS_PER_ENV_STEP = 4356          # SURVEY.md §8d, HoleReacher/ProMP (FMA = 2, each collision test once per step)
 TRAJ_BYTES_PER_ENV = 2 * 200 * 5 * 4 + N_PARAMS * 4   # fg_trajgen: pos + vel out, params in
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at
+# the same sizes (profiles/r1_rollout_ncu_summary.txt, profiles/r1_trajgen_ncu_summary.txt)
+NCU_TRAFFIC_ROLLOUT = 14_334_720 + 3_072
+NCU_TRAFFIC_TRAJGEN = 26_348_288 + 2_040_126_000
 
 
 # ------------------------------------------------------------------------------------------------
@@ -343,7 +347,8 @@ def main():
     steps_per_launch = env_steps / K
     achieved = OPS_PER_ENV_STEP * steps_per_launch / (kernel_ms * 1e-3) / 1e12
     roofline = dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak if fp32_peak else None,
-                    traffic=None, kernel="k_rollout<HOLE_REACHER, PROMP, vel, 5>", kernel_ms=kernel_ms,
+                    traffic=NCU_TRAFFIC_ROLLOUT if B == B_PER_GPU else None, traffic_unit="bytes per launch (ncu dram read + write)",
+                    kernel="k_rollout<HOLE_REACHER, PROMP, vel, 5>", kernel_ms=kernel_ms,
                     peak_source="FFMA chain probe measured in this run (fg_ffma_probe); MEASURED_PEAKS.json has no CUDA-core figure",
                     note="achieved counts ALGORITHMIC ops: 4356 per env step incl. the literal 500 wall samples; the kernel uses an "
                          "exact-equivalent interval search, so frac is not a pipe utilisation (see profiles/ for ncu pipe numbers)")
@@ -368,7 +373,8 @@ def main():
     del outs
     traj_ms = sum(a.elapsed_time(b) for a, b in tev) / reps        # average launch duration over the timed launches
     traj_gbs = Bt * TRAJ_BYTES_PER_ENV / (traj_ms * 1e-3) / 1e9
-    roofline_traj = dict(bound="hbm", achieved=traj_gbs, peak=hbm_peak, unit="GB/s", frac=traj_gbs / hbm_peak, traffic=None,
+    roofline_traj = dict(bound="hbm", achieved=traj_gbs, peak=hbm_peak, unit="GB/s", frac=traj_gbs / hbm_peak,
+                         traffic=NCU_TRAFFIC_TRAJGEN, traffic_unit="bytes per launch (ncu dram read + write; algorithmic: %d)" % (Bt * TRAJ_BYTES_PER_ENV),
                          kernel="k_trajgen_closed<PROMP,5,5>", kernel_ms=traj_ms, peak_source=hbm_src,
                          trajectories_per_s=Bt / (traj_ms * 1e-3), workload=f"{Bt} ProMP trajectories [200,5] pos+vel (2.1 GB output, > L2)")
 

@@ -423,7 +423,6 @@ class BlackBoxWrapper(Wrapper):
         else:
             obs, info = self.env.reset(seed=seed, options={k: v for k, v in (options or {}).items() if k != "as_numpy"} or None)
             obs = self.observation(obs).contiguous()
-        self._obs.copy_(obs)        # what a frozen env would report; the returned tensor is the caller's own
         as_numpy = (options or {}).get("as_numpy", self.num_envs == 1)
         if as_numpy:
             obs = obs.cpu().numpy()

@@ -7,12 +7,13 @@
 //     tensor core reads anyway — and x_lo = x - x_hi, exact in float32; the dropped A_lo*B_lo term is ~2^-22 relative)
 // so K' = 3*Kc padded to a multiple of 8 = 2..3 tcgen05.mma.kind::tf32 instructions (K = 8 each) per 128 x 256 tile.
 //
-// One CTA per (env, d1, 128-row tile), 6 warps:
+// One CTA per (env, d1, 128-row tile), 9 warps:
 //   all      build the Sigma_w slab, G_d1 and the operand tiles in shared memory (canonical K-major, no-swizzle core matrices)
-//   warp 4   allocates 512 TMEM columns (two 128 x 256 fp32 accumulators), one lane issues the MMAs for n-tile i+1 while
-//   warps 0-3  drain n-tile i: tcgen05.ld (32 lanes x 32 columns) -> + regulariser on the diagonal -> 128B-swizzled staging
-//            tile in shared memory -> ONE 3-D TMA tensor store per 32 x 32 block (cp.async.bulk.tensor), which also clips
-//            rows >= T and columns >= dof*T.
+//   warp 8   allocates 512 TMEM columns (two 128 x 256 fp32 accumulators), one lane issues the MMAs for n-tile i+1 while
+//   warps 0-7  drain n-tile i (warp w: TMEM lane quarter w % 4, column half w / 4): tcgen05.ld (32 lanes x 32 columns, the
+//            next batch is already in flight) -> + regulariser on the diagonal -> 128B-swizzled staging tile in shared
+//            memory -> ONE 3-D TMA tensor store per 32 x 32 block (cp.async.bulk.tensor), which also clips rows >= T and
+//            columns >= dof*T.
 // Synchronisation: mbarriers full[2] (tcgen05.commit -> epilogue) and empty[2] (epilogue -> MMA issuer).
 // The matrix is store bound (4 bytes out per 2*Kc flop): the tensor pipe is idle most of the time by construction; the
 // point of this path is that the SM's CUDA cores only move data (profiles/README.md has the measured pipe utilisations).
@@ -24,7 +25,8 @@
 
 namespace fg {
 
-constexpr int kUmmaThreads = 192;     // warps 0-3: epilogue (TMEM lane quarters), warp 4: MMA issuer, warp 5: helper
+constexpr int kUmmaThreads = 288;     // warps 0-7: epilogue (TMEM lane quarter w % 4, column half w / 4), warp 8: MMA issuer
+constexpr int kUmmaEpiWarps = 8;
 constexpr int kUmmaM = 128, kUmmaN = 256;
 
 namespace umma {
@@ -79,8 +81,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {      // implies tcgen05.fence::before_thread_sync
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -90,10 +91,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -112,8 +111,8 @@ __host__ __device__ inline UmmaSmem umma_smem_plan(int Kc, int N, int T) {
   const int D = N * Kc, NT = N * T;
   s.KK = ((3 * Kc + 7) / 8) * 8;
   s.n_pad = ((NT + kUmmaN - 1) / kUmmaN) * kUmmaN;
-  s.off_stage = 0;                                        // 4 warps x 2 buffers x 4 KB, 1024-byte aligned (128B swizzle)
-  s.off_a = s.off_stage + 4 * 2 * 4096;                   // A' [KK/4 chunks][16 row groups][8 rows][16 B]
+  s.off_stage = 0;                                        // 8 warps x 2 buffers x 4 KB, 1024-byte aligned (128B swizzle)
+  s.off_a = s.off_stage + kUmmaEpiWarps * 2 * 4096;       // A' [KK/4 chunks][16 row groups][8 rows][16 B]
   s.off_b = s.off_a + kUmmaM * s.KK * 4;                  // B' [KK/4 chunks][n_pad/8 row groups][8 rows][16 B]
   s.off_misc = s.off_b + s.n_pad * s.KK * 4;              // mbarriers (4 x 8 B) + TMEM base (4 B)
   s.off_f32 = s.off_misc + 64;                            // Ls [D*D], Bs [T*Kc], Ss [Kc*D], Gs [Kc*NT]
@@ -143,12 +142,12 @@ k_cov_umma(const __grid_constant__ CovArgs a, const __grid_constant__ CUtensorMa
   const int d1 = blockIdx.y, m0 = blockIdx.x * kUmmaM;
 
   // ---- TMEM allocation + barriers (warp 4) while the other warps start on the operands ----
-  if (warp == 4) {
+  if (warp == kUmmaEpiWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
       mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);       // full: one tcgen05.commit
-      mbar_init(&bars[2], 4); mbar_init(&bars[3], 4);       // empty: the four epilogue warps
+      mbar_init(&bars[2], kUmmaEpiWarps); mbar_init(&bars[3], kUmmaEpiWarps);     // empty: the epilogue warps
       fence_barrier_init();
     }
   }
@@ -208,7 +207,7 @@ k_cov_umma(const __grid_constant__ CovArgs a, const __grid_constant__ CUtensorMa
   const int n_tiles = n_pad / kUmmaN;
   const float regterm = a.reg * (a.batch_scope ? *a.gmax : a.envmax[b]);
 
-  if (warp == 4) {
+  if (warp == kUmmaEpiWarps) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = instr_desc_tf32(kUmmaM, kUmmaN);
@@ -226,23 +225,32 @@ k_cov_umma(const __grid_constant__ CovArgs a, const __grid_constant__ CUtensorMa
         mma_commit(&bars[buf]);
       }
     }
-  } else if (warp < 4) {
+  } else {
     // ===== epilogue: TMEM -> registers -> swizzled staging tile -> TMA tensor store =====
-    const int row = warp * 32 + lane, t1 = m0 + row;
-    const bool warp_has_rows = m0 + warp * 32 < T;
+    const int quarter = warp & 3, half = warp >> 2;            // TMEM lanes 32*quarter.., columns 128*half.. of each tile
+    const int row = quarter * 32 + lane, t1 = m0 + row;
+    const bool warp_has_rows = m0 + quarter * 32 < T;
     const int diag_col = d1 * T + t1;
     float* st = stage + warp * 2 * 1024;
+    constexpr int kBatches = kUmmaN / 2 / 32;                   // 32-column batches per warp and tile
     int sbuf = 0;
     for (int i = 0; i < n_tiles; ++i) {
       const int buf = i & 1;
       mbar_wait(&bars[buf], (i >> 1) & 1);
       tc_fence_after();
-      for (int j = 0; j < kUmmaN / 32; ++j) {
-        const int col0 = i * kUmmaN + j * 32;
-        if (col0 >= NT) break;                         // uniform: nothing valid further right
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kUmmaN + j * 32), v);
-        if (warp_has_rows) {
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kUmmaN + half * (kUmmaN / 2));
+      const int tile_col0 = i * kUmmaN + half * (kUmmaN / 2);
+      uint32_t r[2][32];
+      tmem_ld32_issue(t_addr, r[0]);
+#pragma unroll
+      for (int j = 0; j < kBatches; ++j) {
+        const int col0 = tile_col0 + j * 32;
+        tmem_ld_wait();                                          // batch j has landed in r[j & 1]
+        if (j + 1 < kBatches) tmem_ld32_issue(t_addr + (j + 1) * 32, r[(j + 1) & 1]);      // batch j+1 in flight meanwhile
+        if (warp_has_rows && col0 < NT) {
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[j & 1][q]);
           const int e = diag_col - col0;
           if (e >= 0 && e < 32) {
 #pragma unroll
@@ -258,7 +266,7 @@ k_cov_umma(const __grid_constant__ CovArgs a, const __grid_constant__ CUtensorMa
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&out_map, sb, col0, m0 + warp * 32, (int)(b * N + d1));
+            tma_store_3d(&out_map, sb, col0, m0 + quarter * 32, (int)(b * N + d1));
             bulk_commit();
           }
           sbuf ^= 1;
@@ -272,7 +280,7 @@ k_cov_umma(const __grid_constant__ CovArgs a, const __grid_constant__ CUtensorMa
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kUmmaEpiWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }

@@ -35,7 +35,7 @@ __host__ __device__ inline size_t rollout_smem_floats(int T, int cols_a, int row
 // KC == 0: run-time K; weights stay in shared memory (k-major, thread-minor: conflict free).
 // DBG: the verbose>=2 variant that also writes the per-step actions / observations / rewards (black_box_wrapper.py:208-213).
 #ifndef FG_ROLLOUT_MINB
-#define FG_ROLLOUT_MINB 1
+#define FG_ROLLOUT_MINB 4   // <= 128 registers: 4 blocks of 128 threads per SM (65 536 envs need 443 resident threads per SM)
 #endif
 template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
 __global__ void __launch_bounds__(kRolloutThreads, FG_ROLLOUT_MINB)

@@ -82,3 +82,28 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
                     bad.append(os.path.join(r, f))
     assert not bad, bad
+
+
+def test_hot_kernels_keep_their_register_budget():
+    """Occupancy guard (no GPU needed): the fused HoleReacher/ProMP rollout must stay <= 128 registers per thread (4 blocks
+    of 128 threads per SM: 65,536 envs need 443 resident threads per SM), the covariance kernel <= 64."""
+    import shutil
+    from fancy_gym_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "--dump-resource-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    hot = [n for n in regs if "k_rolloutILi0ELi0ELb0ELi5ELi5ELb0" in n]
+    assert hot and all(regs[n] <= 128 for n in hot), {n: regs[n] for n in hot}
+    assert all(v <= 128 for n, v in regs.items() if "k_rollout" in n), "a rollout instantiation exceeds 128 registers"
+    cov = [n for n in regs if "k_cov_simtILi5" in n]
+    assert cov and all(regs[n] <= 64 for n in cov)
