@@ -416,6 +416,30 @@ def main():
                ms_per_step=1e3 * float(te2e.item()) / K,
                api="fancy_gym_b200.make(...).reset() + .step(params from pinned host memory) + D2H of return/length/terminated")
 
+    # ---------------- the same end-to-end step replayed as ONE CUDA graph (extra; the headline e2e stays the eager API) -----
+    e2e_graph = None
+    try:
+        runner = fancy_gym.GraphedEpisode(env)
+        runner.host_params.copy_(host_params[0])
+        for _ in range(W):
+            runner.run()
+        sync_all()
+        t0 = time.perf_counter()
+        g_steps = 0
+        for i in range(K):       # (an optimiser writes its samples straight into runner.host_params; H2D is part of the graph)
+            g_steps += int(runner.run()[1].sum())
+        sync_all()
+        g_s = time.perf_counter() - t0
+        tg = torch.tensor([g_s], dtype=torch.float64, device=dev)
+        ng = torch.tensor([float(g_steps)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ng, op=dist.ReduceOp.SUM)
+        e2e_graph = dict(value=float(ng.item()) / float(tg.item()), unit="env-steps/s", ms_per_step=1e3 * float(tg.item()) / K,
+                         api="fancy_gym_b200.GraphedEpisode(env).run(): reset + H2D + rollout + D2H as one cudaGraphLaunch")
+    except Exception as e:      # noqa: BLE001  (an extra; never fails the bench)
+        e2e_graph = dict(error=repr(e))
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -433,7 +457,7 @@ def main():
                                 l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
                                 collective="all_gather(return,length,flags) per step" if world > 1 else "none"),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
-                    roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e,
+                    roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_graph=e2e_graph,
                     clocks=clk.summary(), gpu_launches=K)
         print(json.dumps(line))
     if world > 1:

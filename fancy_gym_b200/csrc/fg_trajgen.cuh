@@ -102,6 +102,13 @@ k_trajgen_closed(const __grid_constant__ DevCfg c, const float* __restrict__ par
   };
 
   long long b = (long long)blockIdx.x * envs_per_block + warp;
+#ifdef FG_TRAJ_NOPREFETCH
+  float w[N][KWC];
+  for (; b < b_end; b += warps_total) {
+    if constexpr (KW > 0) {
+      load_weights(b, w);
+    } else {
+#else
   float w[N][KWC], wn[N][KWC];
   if constexpr (KW > 0) {
     if (b < b_end) load_weights(b, wn);
@@ -114,6 +121,7 @@ k_trajgen_closed(const __grid_constant__ DevCfg c, const float* __restrict__ par
         for (int k = 0; k < KWC; ++k) w[d][k] = wn[d][k];
       if (b + warps_total < b_end) load_weights(b + warps_total, wn);     // prefetch: in flight while this env is evaluated
     } else {
+#endif
       __syncwarp();
       load_weights(b, w);
       __syncwarp();

@@ -264,3 +264,26 @@ def test_partial_reset_only_touches_masked_envs(fg):
     keep = mask == 0
     assert torch.equal(base.ctx[keep], ctx0[keep]) and torch.equal(base.q[keep], q0[keep])
     assert not torch.equal(base.ctx[~keep], ctx0[~keep])
+
+
+def test_graphed_episode_replays_the_eager_episode(fg):
+    """GraphedEpisode (reset + H2D + rollout + D2H as one CUDA graph) == the same calls made eagerly, episode after episode"""
+    import torch
+    B = 2048
+    eager = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
+    graphed = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
+    eager.reset(seed=11)
+    graphed.reset(seed=11)
+    runner = fg.GraphedEpisode(graphed, warmup=2)          # the 2 warm-up episodes advance every env's context stream
+    for _ in range(2):                                      # (the capture itself only records, it does not execute)
+        eager.reset(seed=None)
+    gen = torch.Generator().manual_seed(0)
+    for it in range(3):
+        p = 0.5 * torch.randn(B, 25, generator=gen)
+        runner.host_params.copy_(p)
+        ret, length, term = runner.run()
+        obs0, _ = eager.reset(seed=None)
+        _, e_ret, e_term, _, e_info = eager.step(p.to(DEV))
+        assert torch.equal(runner.host_obs, obs0.cpu())
+        assert torch.equal(ret, e_ret.cpu()) and torch.equal(length, e_info["trajectory_length"].cpu())
+        assert torch.equal(term, e_term.cpu())
