@@ -15,12 +15,13 @@ import torch
 
 
 class GraphedEpisode:
-    def __init__(self, env, warmup: int = 3):
+    def __init__(self, env, warmup: int = 3, copy_obs: bool = False):
         if env.do_replanning or env.learn_sub_trajectories:
             raise NotImplementedError("GraphedEpisode captures one plan per episode")
         if not env._fast_reset:
             raise NotImplementedError("GraphedEpisode needs the device-side reset (context_sampler='device')")
         self.env = env
+        self.copy_obs = bool(copy_obs)      # also bring the context observation of every episode to the host
         dev = env.device
         B, P = env.num_envs, env.action_space.shape[0]
         self.host_params = torch.zeros(B, P, dtype=torch.float32).pin_memory()
@@ -47,7 +48,8 @@ class GraphedEpisode:
         obs0, _ = env.reset(seed=None, options={"as_numpy": False})
         self._params.copy_(self.host_params, non_blocking=True)
         _obs, ret, terminated, _trunc, info = env.step(self._params)
-        self.host_obs.copy_(obs0, non_blocking=True)                  # the context observation the parameters answer to
+        if self.copy_obs:
+            self.host_obs.copy_(obs0, non_blocking=True)              # the context observation the parameters answer to
         self.host_ret.copy_(ret, non_blocking=True)
         self.host_len.copy_(info["trajectory_length"], non_blocking=True)
         self.host_terminated.copy_(terminated, non_blocking=True)

@@ -274,7 +274,7 @@ def test_graphed_episode_replays_the_eager_episode(fg):
     graphed = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
     eager.reset(seed=11)
     graphed.reset(seed=11)
-    runner = fg.GraphedEpisode(graphed, warmup=2)          # the 2 warm-up episodes advance every env's context stream
+    runner = fg.GraphedEpisode(graphed, warmup=2, copy_obs=True)          # the 2 warm-up episodes advance every env's context stream
     for _ in range(2):                                      # (the capture itself only records, it does not execute)
         eager.reset(seed=None)
     gen = torch.Generator().manual_seed(0)
