@@ -100,15 +100,22 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   }
 
   // ---- per-env state ----
+  // Velocity state.  In the velocity-controlled envs with a float32 action (velocity / position controller) the joint
+  // velocity IS the last float32 action (or the zeros of reset), so it is carried as float32: no conversions per step and
+  // ten registers less; it is float64 only at the HBM boundary.  PD-controlled / torque envs keep the float64 value.
+  constexpr bool VF = !MOTOR && (ENV == FG_ENV_HOLE_REACHER || ENV == FG_ENV_VIAPOINT_REACHER);
   double q[N], v[N];
+  float vf[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     if constexpr (ENV == FG_ENV_TOY) {   // ToyWrapper: current_pos = 1, current_vel = 0 (test_black_box.py:48-56)
       q[i] = 1.0;
       v[i] = 0.0;
+      vf[i] = 0.f;
     } else {
       q[i] = io.q[b * N + i];
       v[i] = io.v[b * N + i];
+      vf[i] = (float)v[i];
     }
   }
   int steps = io.steps[b];
@@ -147,7 +154,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
       for (int i = 0; i < N; ++i) obs[N + i] = (float)sin(q[i]);
 #pragma unroll
-      for (int i = 0; i < N; ++i) obs[2 * N + i] = (float)v[i];
+      for (int i = 0; i < N; ++i) obs[2 * N + i] = VF ? vf[i] : (float)v[i];
       no = 3 * N;
       if constexpr (ENV == FG_ENV_HOLE_REACHER) {
         obs[no++] = (float)cx1;
@@ -177,7 +184,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       vbc[i] = io.cond_vel[b * N + i];
     } else {
       ybc[i] = (float)q[i];
-      vbc[i] = (float)v[i];
+      vbc[i] = VF ? vf[i] : (float)v[i];
     }
   }
 
@@ -327,21 +334,21 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       if (MOTOR || steps == 0) {      // v is float64 (zeros at reset / float64 actions): float64 arithmetic
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const double ac = (a64[i] - v[i]) / c.dt;
+          const double ac = (a64[i] - (VF ? (double)vf[i] : v[i])) / c.dt;
           acc_cost += ac * ac;
         }
       } else {                        // float32 action and float32 velocity
         float s32 = 0.f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const float ac = div_by(__fsub_rn(a32[i], (float)v[i]), c.dt_f, r_dt);
+          const float ac = div_by(__fsub_rn(a32[i], VF ? vf[i] : (float)v[i]), c.dt_f, r_dt);
           s32 = __fadd_rn(s32, __fmul_rn(ac, ac));
         }
         acc_cost = (double)s32;
       }
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        v[i] = a64[i];
+        if constexpr (VF) vf[i] = a32[i]; else v[i] = a64[i];
         q[i] += MOTOR ? __dmul_rn(c.dt, a64[i]) : (double)__fmul_rn(c.dt_f, a32[i]);
       }
     } else if constexpr (ENV == FG_ENV_SIMPLE_REACHER) {
@@ -528,7 +535,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       io.q[b * N + i] = q[i];
-      io.v[b * N + i] = v[i];
+      io.v[b * N + i] = VF ? (double)vf[i] : v[i];
     }
   }
   io.steps[b] = steps;
