@@ -143,6 +143,18 @@ __device__ __forceinline__ bool self_hits(const double (&th)[N], const float (&c
 // unless every one of them is farther than 8e-6 from zero — i.e. unless some links are (nearly) collinear —
 // the decisions are already those of the accurate evaluation, which is only entered otherwise.
 template <int N>
+struct Angles {
+  double th[N];
+};
+// the accurate evaluation is rare (nearly collinear links): kept out of the hot loop body, angles passed by value
+template <int N>
+__device__ __noinline__ bool self_hits_accurate(const Angles<N> a) {
+  const float zero[N] = {};
+  float unused;
+  return self_hits<N, true>(a.th, zero, zero, unused);
+}
+
+template <int N>
 __device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N], const float (&cs)[N],
                                                const float (&sn)[N]) {
   bool lim = false;
@@ -153,7 +165,12 @@ __device__ __forceinline__ bool self_collision(const double (&q)[N], const doubl
   } else {
     float min_abs;
     bool hit = self_hits<N, false>(th, cs, sn, min_abs);
-    if (min_abs <= 8e-6f) hit = self_hits<N, true>(th, cs, sn, min_abs);
+    if (min_abs <= 8e-6f) {
+      Angles<N> a;
+#pragma unroll
+      for (int i = 0; i < N; ++i) a.th[i] = th[i];
+      hit = self_hits_accurate<N>(a);
+    }
     return lim | hit;
   }
 }
@@ -204,8 +221,9 @@ __device__ __forceinline__ bool overlap3(Span a, Span b, Span c) {
   return max(max(a.lo, b.lo), c.lo) < min(min(a.hi, b.hi), c.hi);
 }
 
-__device__ __forceinline__ bool link_wall_search(const float* __restrict__ s_m, float c, float s, float X, float Y,
-                                                 const Hole& h) {
+// (out of line: up to N calls per step share ONE copy of the six unrolled searches — the fused kernel's loop body
+//  otherwise exceeds the instruction cache; measured "no_instruction" stalls, profiles/README.md)
+static __device__ __noinline__ bool link_wall_search(const float* __restrict__ s_m, float c, float s, float X, float Y, const Hole h) {
   const bool rx = c < 0.f, ry = s < 0.f;
   const Span A = span_below(count_below<false>(s_m, c, X, h.xl, rx), rx);          // x <  xl
   const Span Bx = span_above(count_below<true>(s_m, c, X, h.xr, rx), rx);          // x >  xr
@@ -216,8 +234,7 @@ __device__ __forceinline__ bool link_wall_search(const float* __restrict__ s_m, 
   return overlap(A, C) | overlap(Bx, C) | overlap3(Gl, Lr, D);
 }
 
-__device__ __forceinline__ bool link_wall_brute(const float* __restrict__ s_m, float c, float s, float X, float Y,
-                                                const Hole& h) {
+static __device__ __noinline__ bool link_wall_brute(const float* __restrict__ s_m, float c, float s, float X, float Y, const Hole h) {
   bool hit = false;
 #pragma unroll 4
   for (int m = 0; m < kLinePoints; ++m) {
@@ -252,16 +269,26 @@ __device__ __forceinline__ bool wall_collision(const float* __restrict__ s_m, co
 // float64 forward kinematics of the end effector, for the steps on which the reference *reports*
 // a distance / end effector / observation (base_reacher.py:95-103, :137-139)
 template <int N>
-__device__ __forceinline__ void end_effector64(const double (&th)[N], double& ex, double& ey) {
-  ex = 0.0;
-  ey = 0.0;
+__device__ __noinline__ double2 end_effector64_ool(const Angles<N> a) {
+  double ex = 0.0, ey = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double s, c;
-    sincos(th[i], &s, &c);
+    sincos(a.th[i], &s, &c);
     ex += c;
     ey += s;
   }
+  return make_double2(ex, ey);
+}
+// executed on a handful of steps per episode: one out-of-line copy instead of three inlined double-precision sincos chains
+template <int N>
+__device__ __forceinline__ void end_effector64(const double (&th)[N], double& ex, double& ey) {
+  Angles<N> a;
+#pragma unroll
+  for (int i = 0; i < N; ++i) a.th[i] = th[i];
+  const double2 e = end_effector64_ool<N>(a);
+  ex = e.x;
+  ey = e.y;
 }
 
 }  // namespace fg
