@@ -41,8 +41,8 @@ OPS_PER_ENV_STEP = 4356          # SURVEY.md §8d, HoleReacher/ProMP (FMA = 2, e
 TRAJ_BYTES_PER_ENV = 2 * 200 * 5 * 4 + N_PARAMS * 4   # fg_trajgen: pos + vel out, params in
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at
 # the same sizes (profiles/r1_rollout_ncu_summary.txt, profiles/r1_trajgen_ncu_summary.txt)
-NCU_TRAFFIC_ROLLOUT = 14_334_720 + 3_072
-NCU_TRAFFIC_TRAJGEN = 26_348_288 + 2_040_126_000
+NCU_TRAFFIC_ROLLOUT = 14_296_576 + 1_024
+NCU_TRAFFIC_TRAJGEN = 26_361_856 + 2_041_428_000
 
 
 # ------------------------------------------------------------------------------------------------
