@@ -157,9 +157,13 @@ __device__ __noinline__ bool self_hits_accurate(const Angles<N> a) {
 template <int N>
 __device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N], const float (&cs)[N],
                                                const float (&sn)[N]) {
+  // any(q > pi) or any(q < -pi): |q| > pi as an unsigned compare of the sign-stripped bit patterns (non-negative doubles
+  // order like integers) — two integer compares per joint instead of the double-precision max chain ptxas builds
   bool lim = false;
+  constexpr unsigned long long kPiBits = 0x400921FB54442D18ULL;
 #pragma unroll
-  for (int i = 0; i < N; ++i) lim |= fabs(q[i]) > kPi;      // any(q > pi) or any(q < -pi)
+  for (int i = 0; i < N; ++i)
+    lim |= ((unsigned long long)__double_as_longlong(q[i]) & 0x7FFFFFFFFFFFFFFFULL) > kPiBits;
   if constexpr (N < 3) {
     return lim;
   } else {
@@ -249,19 +253,30 @@ template <int N>
 __device__ __forceinline__ bool wall_collision(const float* __restrict__ s_m, const float (&cs)[N],
                                                const float (&sn)[N], const Hole& h, int wall_mode) {
   bool hit = false;
-  float X = 0.f, Y = 0.f;
   const float ythr = fmaxf(0.f, h.nd);
+  // joint positions first, then ONE test whether any link reaches below the ground line at all (the common case in the
+  // sigma = 0.25 regime is "none": a single branch instead of N divergent ones)
+  float Xs[N], Ys[N];
+  unsigned below = 0;
+  {
+    float X = 0.f, Y = 0.f;
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const float X1 = fmaf(cs[i], 1.0f, X), Y1 = fmaf(sn[i], 1.0f, Y);   // sample m=99 (s=1) == next joint
-    if (fminf(Y, Y1) < ythr) {
-      hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], X, Y, h)
-                              : link_wall_brute(s_m, cs[i], sn[i], X, Y, h);
-    } else if (wall_mode == 2) {
-      hit |= link_wall_brute(s_m, cs[i], sn[i], X, Y, h);   // mode 2: no skipping at all
+    for (int i = 0; i < N; ++i) {
+      Xs[i] = X;
+      Ys[i] = Y;
+      const float Y1 = fmaf(sn[i], 1.0f, Y);      // sample m=99 (s=1) == next joint
+      below |= (fminf(Y, Y1) < ythr) ? (1u << i) : 0u;
+      X = fmaf(cs[i], 1.0f, X);
+      Y = Y1;
     }
-    X = X1;
-    Y = Y1;
+  }
+  if (wall_mode == 2) below = (1u << N) - 1;      // mode 2: no skipping at all
+  if (below) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (below & (1u << i))
+        hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], Xs[i], Ys[i], h)
+                                : link_wall_brute(s_m, cs[i], sn[i], Xs[i], Ys[i], h);
   }
   return hit;
 }
