@@ -419,6 +419,8 @@ def main():
     # ---------------- the same end-to-end step replayed as ONE CUDA graph (extra; the headline e2e stays the eager API) -----
     e2e_graph = None
     try:
+        if world > 1:
+            raise RuntimeError("skipped for N > 1 (an extra of the single-GPU line)")
         runner = fancy_gym.GraphedEpisode(env)
         runner.host_params.copy_(host_params[0])
         for _ in range(W):

@@ -40,7 +40,8 @@ class GraphedEpisode:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread-local capture mode: CUDA calls of other threads (e.g. NCCL's watchdog) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._episode()
 
     def _episode(self):
