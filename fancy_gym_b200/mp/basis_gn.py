@@ -136,8 +136,12 @@ class ProDMPBasisGenerator(NormalizedRBFBasisGenerator):
         self.auto_basis_scale_factors = 1.0 / np.abs(self.pc_pos_basis).max(axis=0)
 
     def indices(self, times) -> np.ndarray:
+        # float32 like the library: torch.round(left_bound_linear_phase(times) / scaled_dt), scaled_dt = dt / tau0 a float32
+        # tensor; ties (k * tau0 / tau = x.5, e.g. tau0 1.5 and a learned tau of 0.8) depend on that rounding
         pg = self.phase_generator
-        z = np.maximum((np.asarray(times, dtype=np.float64) - pg.scalar_delay()) / pg.scalar_tau(), 0)
+        f32 = np.float32
+        z = np.maximum((np.asarray(times).astype(f32) - f32(pg.scalar_delay())) / f32(pg.scalar_tau()), f32(0)).astype(f32)
         if z.size and z.max() > self.pre_compute_length_factor:
             raise RuntimeError("Time is beyond the pre-computation range.")
-        return np.rint(z / self.scaled_dt).astype(np.int64)
+        sd32 = f32(f32(self.dt) / f32(pg._tau0))
+        return np.rint((z / sd32).astype(f32)).astype(np.int64)

@@ -101,7 +101,7 @@ class MPInterface:
     def set_duration(self, duration, dt):
         self.dt = float(dt)
         if duration is None:     # learn_sub_trajectories: trajectory length follows the learned tau
-            if not self.phase_gn.uniform():
+            if not self.phase_gn.collapse_if_equal():
                 # one plan length per launch: the batch must agree on round(tau / dt) (this reads tau back to the host)
                 tau = self.phase_gn.tau.detach().cpu()
                 steps = torch.round(tau / dt)
@@ -193,7 +193,7 @@ class MPInterface:
             pos, vel = out
             assert pos.shape == (B, T, N) and vel.shape == (B, T, N) and pos.is_contiguous() and vel.is_contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        if self.phase_gn.uniform():
+        if self.phase_gn.uniform() or (self.mp_kind == _lib.MP_PRODMP and self.phase_gn.collapse_if_equal()):
             _lib.check(_lib.lib.fg_trajgen(self._trajgen_handle(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
                                            bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(), B,
                                            C.c_void_p(stream)))

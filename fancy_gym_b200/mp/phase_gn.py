@@ -82,6 +82,18 @@ class PhaseGenerator:
     def scalar_delay(self) -> float:
         return float(self.delay) if self.delay.dim() == 0 else self._delay0
 
+    def collapse_if_equal(self) -> bool:
+        """If every env of the batch carries the same tau and the same delay, store them as shared scalars (table-driven
+        kernels).  Reads the values back to the host: used where the host needs them anyway (sub-trajectory lengths)
+        or where no per-env kernel exists (ProDMP).  Returns uniform()."""
+        for name in ("tau", "delay"):
+            x = getattr(self, name)
+            if x.dim() > 0:
+                xc = x.detach().cpu().reshape(-1)
+                if bool((xc == xc[0]).all()):
+                    setattr(self, name, xc[0].clone())
+        return self.uniform()
+
     def per_env(self, num_envs: int, device):
         """(tau [B], delay [B]) float32 on the device"""
         def expand(x):

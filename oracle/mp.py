@@ -314,7 +314,11 @@ class ProDMPBasis(NormalizedRBFBasis):
             raise RuntimeError("Time is beyond the pre-computation range.")
         idx = z / self.scaled_dt
         if not self.interpolate:
-            return table[np.rint(idx).astype(np.int64)]
+            # the library rounds in float32: torch.round(scaled_times / self.scaled_dt) with both operands float32
+            # (scaled_dt = dt / tau0 is a float32 tensor); ties (k * tau0 / tau = x.5) depend on that rounding
+            z32 = self.phase_generator.left_bound_linear_phase(np.asarray(times)).astype(F32)
+            sd32 = F32(F32(self.dt) / F32(self.phase_generator.tau0))
+            return table[np.rint((z32 / sd32).astype(F32)).astype(np.int64)]
         i0 = np.clip(np.floor(idx).astype(np.int64), 0, table.shape[0] - 2)
         fr = (idx - i0)[..., None]
         return table[i0] * (1 - fr) + table[i0 + 1] * fr

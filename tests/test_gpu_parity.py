@@ -441,3 +441,45 @@ def test_step_results_stay_valid_for_one_more_step():
     # terminated / truncated are exactly the flag bits
     assert torch.equal(te2, (env._flags & 1) != 0) and torch.equal(tr2, (env._flags & 2) != 0)
     assert torch.equal(info2["is_success"], (env._flags & 4) != 0) and torch.equal(info2["is_collided"], (env._flags & 8) != 0)
+
+
+# --------------------------------------------------------------------------------------------
+# sequencing (learn_sub_trajectories, BASELINE config 4's second variant): every black-box step plans a sub-trajectory
+# whose length follows the learned tau; the batch shares tau per step, tau changes from step to step
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_id", ["fancy_ProDMP/SimpleReacher-v0", "fancy_ProMP/HoleReacher-v0", "fancy_DMP/ViaPointReacher-v0"])
+def test_sub_trajectory_sequencing_matches_oracle(env_id):
+    fancy_gym = _fg()
+    B = 129
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override={"black_box_kwargs": {"learn_sub_trajectories": True}})
+    orc = make_oracle(env_id, mode="mirror", learn_sub_trajectories=True)
+    obs0, _ = env.reset(seed=21, options={"as_numpy": True})
+    o_obs0 = orc.reset(seeds=21 + np.arange(B))
+    assert np.allclose(obs0, o_obs0, atol=1e-6) and obs0.shape[1] == env.observation_space.shape[0]
+    rng = np.random.default_rng(8)
+    P = env.action_space.shape[0]
+    assert P == n_params_of(env_id) + 1                      # tau leads the parameter vector
+    total = np.zeros(B, dtype=np.int64)
+    was_live = np.ones(B, bool)
+    ever_terminated = np.zeros(B, bool)
+    for tau in (0.37, 0.8, 0.55, 2.0):                       # 37 + 80 + 55 steps, then the rest of the 200-step episode
+        params = (0.4 * rng.standard_normal((B, P))).astype(np.float32)
+        params[:, 0] = tau
+        o_obs, o_ret, o_te, o_tr, o_info = orc.step(params)
+        obs, ret, te, tr, info = env.step(params)
+        tie = o_info["min_margin"] < TIE_EPS
+        agree = (info["trajectory_length"] == o_info["trajectory_length"]) & (te == o_te) & (tr == o_tr)
+        assert (agree | tie).all(), (tau, int((~(agree | tie)).sum()))
+        if tie.any() and not agree.all():
+            pytest.skip("a boundary tie resolved differently: the two sides diverge from here on")
+        fin = np.isfinite(o_ret)
+        assert rel_err(ret[fin], o_ret[fin]).max() < 1e-5 if fin.any() else True
+        assert (np.abs(obs - o_obs) <= 2e-5 * np.maximum(1.0, np.abs(o_obs))).all(), tau
+        total += info["trajectory_length"]
+        ran_through = was_live & ~(te | tr)                  # planned this sub-trajectory and neither terminated nor ran out of time
+        if tau < 2.0:
+            assert (info["trajectory_length"][ran_through] == round(tau / 0.01)).all()
+        assert (info["trajectory_length"][~was_live] == 0).all()
+        was_live &= ~(te | tr)
+        ever_terminated |= te
+    assert (total <= 200).all() and (total[~ever_terminated] == 200).all()
