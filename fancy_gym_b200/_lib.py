@@ -53,6 +53,7 @@ class FgResetCfg(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32),
         ("env_kind", C.c_int32), ("n_dof", C.c_int32), ("random_start", C.c_int32), ("time_aware", C.c_int32),
+        ("device", C.c_int32),
         ("fixed", C.c_double * 4), ("has_fixed", C.c_int32 * 4),
         ("n_obs_out", C.c_int32), ("obs_index", C.c_int32 * FG_MAX_OBS),
     ]

@@ -304,9 +304,13 @@ fg_status fg_reset(const fg_reset_cfg* cfg, const fg_reset_io* io, int64_t B, vo
   for (int i = 0; i < 4; ++i) { c.fixed[i] = cfg->fixed[i]; c.has_fixed[i] = cfg->has_fixed[i]; }
   c.n_obs_out = cfg->n_obs_out;
   for (int j = 0; j < cfg->n_obs_out; ++j) c.obs_index[j] = cfg->obs_index[j];
+  int prev = 0;
+  FG_CUDA(cudaGetDevice(&prev));
+  if (prev != cfg->device) FG_CUDA(cudaSetDevice(cfg->device));
   const unsigned blocks = (unsigned)((B + 127) / 128);
   fg::k_reset<<<blocks, 128, 0, (cudaStream_t)stream>>>(c, *io, B);
   const cudaError_t e = cudaGetLastError();
+  if (prev != cfg->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_reset launch: %s", cudaGetErrorString(e));
   return FG_OK;
 }

@@ -160,6 +160,7 @@ class BaseReacherEnv(Env):
         cfg.env_kind, cfg.n_dof = self.env_kind, n
         cfg.random_start = int(bool(self.random_start if random_start is None else random_start))
         cfg.time_aware = int(bool(time_aware))
+        cfg.device = dev.index or 0
         vals, given = self._fixed_context()
         for i in range(4):
             cfg.fixed[i], cfg.has_fixed[i] = float(vals[i]), int(given[i])

@@ -165,6 +165,7 @@ typedef struct fg_reset_cfg {
   int32_t n_dof;
   int32_t random_start;        /* constructor kwarg random_start (base_reacher.py:77-86) */
   int32_t time_aware;          /* append the (zero) elapsed-time column to the observation */
+  int32_t device;              /* CUDA device ordinal the buffers live on */
   /* fixed task context (constructor kwargs hole_x, hole_width, hole_depth | via_target, target | target);
    * has_fixed[i] == 0: entry i is sampled.  Layout as fg_rollout_io.ctx. */
   double fixed[4];

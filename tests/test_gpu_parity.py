@@ -483,3 +483,24 @@ def test_sub_trajectory_sequencing_matches_oracle(env_id):
         was_live &= ~(te | tr)
         ever_terminated |= te
     assert (total <= 200).all() and (total[~ever_terminated] == 200).all()
+
+
+def test_env_on_a_non_current_device():
+    """every entry point selects the device of its buffers itself (one process driving cuda:1 while cuda:0 is current)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fancy_gym = _fg()
+    B = 300
+    torch.cuda.set_device(0)
+    params = (0.5 * np.random.default_rng(0).standard_normal((B, 25))).astype(np.float32)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=dev)
+        env.reset(seed=4)
+        obs, ret, te, tr, info = env.step(torch.as_tensor(params, device=dev))
+        pos, vel = env.get_trajectory(torch.as_tensor(params, device=dev))
+        assert obs.device == torch.device(dev) and pos.device == torch.device(dev)
+        outs.append([x.cpu() for x in (obs, ret, te, info["trajectory_length"], pos, vel)])
+    assert torch.cuda.current_device() == 0
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
