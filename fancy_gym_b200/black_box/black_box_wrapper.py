@@ -284,10 +284,12 @@ class BlackBoxWrapper(Wrapper):
         tg.set_initial_conditions(init_time, self._base.q, self._base.v)   # current_pos / current_vel (:110-111)
         tg.set_duration(duration, self.dt)
 
-    def launch(self, params, seg_steps=None, replan_break=False, dbg=None):
+    def launch(self, params, seg_steps=None, replan_break=False, dbg=None, state=None, keep_state=False):
         """Enqueues ONE fused rollout (fg_rollout) for the current plan on the current CUDA stream and returns
         immediately; results land in the wrapper's device buffers (_ret, _len, _flags, _obs, _info).
-        `params` [B, P_local] float32 on the device (phase parameters already stripped)."""
+        `params` [B, P_local] float32 on the device (phase parameters already stripped).
+        `state`: object with q / v / steps / done / ctx device tensors to start from instead of the env's own;
+        `keep_state=True` leaves that state untouched (evaluate many parameter sets from one start state)."""
         base = self._base
         B = self.num_envs
         T = self.traj_gen.n_steps
@@ -308,8 +310,10 @@ class BlackBoxWrapper(Wrapper):
         io.params = params.data_ptr()
         if per_env_phase:
             io.traj_pos, io.traj_vel = self._traj_buf[0].data_ptr(), self._traj_buf[1].data_ptr()
-        io.ctx = base.ctx.data_ptr()
-        io.q, io.v, io.steps, io.done = base.q.data_ptr(), base.v.data_ptr(), base.steps.data_ptr(), base.done.data_ptr()
+        st = base if state is None else state
+        io.ctx = st.ctx.data_ptr()
+        io.q, io.v, io.steps, io.done = st.q.data_ptr(), st.v.data_ptr(), st.steps.data_ptr(), st.done.data_ptr()
+        io.keep_state = int(bool(keep_state))
         io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
         io.use_cond = int(self.condition_set)
         io.write_cond = (2 if replan_break else 1) if self.condition_on_desired else 0

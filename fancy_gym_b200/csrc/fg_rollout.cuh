@@ -531,15 +531,17 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   const bool stopped = terminated || truncated;
 
   // ---- write back state and results ----
-  if constexpr (ENV != FG_ENV_TOY) {
+  if (!io.keep_state) {
+    if constexpr (ENV != FG_ENV_TOY) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      io.q[b * N + i] = q[i];
-      io.v[b * N + i] = VF ? (double)vf[i] : v[i];
+      for (int i = 0; i < N; ++i) {
+        io.q[b * N + i] = q[i];
+        io.v[b * N + i] = VF ? (double)vf[i] : v[i];
+      }
     }
+    io.steps[b] = steps;
+    io.done[b] = stopped ? 1 : 0;
   }
-  io.steps[b] = steps;
-  io.done[b] = stopped ? 1 : 0;
   if (io.write_cond && len > 0 && (stopped || io.write_cond == 2)) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {

@@ -155,6 +155,8 @@ typedef struct fg_rollout_io {
   /* optional unpacked copies of the flag bits, one byte (0 / 1) per env each, or NULL: what step() returns as
    * terminated / truncated and infos['is_success'] / ['is_collided'] without any post-processing kernel */
   uint8_t* flag_bytes;     /* [4, B]: rows terminated, truncated, success, collided */
+  int32_t keep_state;      /* 1: q / v / steps / done are read but NOT written back: the batch can be evaluated again from the
+                              same start state with other parameters (population-based search on one context) */
 } fg_rollout_io;
 
 /* Episode reset of the classic_control reachers on the device (replaces the host-side samplers
