@@ -329,13 +329,23 @@ class BlackBoxWrapper(Wrapper):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(T if seg_steps is None else seg_steps), C.c_void_p(stream)))
 
-    def step(self, action):
+    def evaluate(self, action):
+        """step() WITHOUT advancing the episode: the same parameters-in / (obs, return, terminated, truncated, infos)-out
+        contract, but the envs stay where they are (fg_rollout keep_state) — a population-based search evaluates
+        candidate after candidate from one reset state / context.  Not available while plans are chained (replanning,
+        sub-trajectories), where a step's outcome is the next step's start."""
+        if self.do_replanning or self.learn_sub_trajectories:
+            raise NotImplementedError("evaluate() is defined for envs that plan once per episode")
+        return self.step(action, _keep_state=True)
+
+    def step(self, action, _keep_state: bool = False):
         base = self._base
         params, as_numpy, scalar = self._prepare_params(action)
         self._set_plan(params)
         local = self.traj_gen.params.contiguous()
         T = self.traj_gen.n_steps
-        self.plan_steps += 1
+        if not _keep_state:
+            self.plan_steps += 1
         seg, replan_break = self._segment_steps(T)
         B, n = self.num_envs, base.n_links
         dbg = None
@@ -346,11 +356,12 @@ class BlackBoxWrapper(Wrapper):
                 dbg["actions"] = torch.zeros(B, T, n, dtype=torch.float64, device=self.device)
                 dbg["obs"] = torch.zeros(B, T, self.env.observation_space.shape[0], dtype=torch.float32, device=self.device)
         planned = self._planned_trajectory(local) if self.verbose >= 2 else None   # before the state moves on
-        self.launch(local, seg, replan_break, dbg)
-        if self.condition_on_desired:
+        self.launch(local, seg, replan_break, dbg, keep_state=_keep_state)
+        if self.condition_on_desired and not _keep_state:
             self.condition_set = True      # every live env breaks at the same step or is done
 
-        self.current_traj_steps += seg     # live envs all advance by `seg`; finished envs are frozen
+        if not _keep_state:
+            self.current_traj_steps += seg     # live envs all advance by `seg`; finished envs are frozen
         length = self._len
         terminated, truncated, success, collided = self._flag_bytes      # written by the kernel: no unpacking ops
         ret = self._ret

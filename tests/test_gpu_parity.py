@@ -504,3 +504,28 @@ def test_env_on_a_non_current_device():
     assert torch.cuda.current_device() == 0
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_evaluate_leaves_the_envs_where_they_are():
+    """evaluate(params) == what step(params) would return, but the episode does not advance: candidates can be compared on
+    one reset state; a following step() with the same parameters returns the identical result."""
+    fancy_gym = _fg()
+    B = 777
+    for env_id in ("fancy_ProMP/HoleReacher-v0", "fancy_DMP/ViaPointReacher-v0", "fancy_ProDMP/SimpleReacher-v0"):
+        env = fancy_gym.make(env_id, num_envs=B, device="cuda:0")
+        env.reset(seed=2)
+        base = env.unwrapped
+        q0, steps0 = base.q.clone(), base.steps.clone()
+        gen = torch.Generator(device="cuda:0").manual_seed(1)
+        P = env.action_space.shape[0]
+        p1, p2 = (0.5 * torch.randn(B, P, generator=gen, device="cuda:0") for _ in range(2))
+        e1 = [x.clone() for x in env.evaluate(p1)[:4]]
+        e2 = [x.clone() for x in env.evaluate(p2)[:4]]
+        assert torch.equal(base.q, q0) and torch.equal(base.steps, steps0) and int(base.done.max()) == 0
+        e1b = env.evaluate(p1)[:4]
+        for a, b in zip(e1, e1b):
+            assert torch.equal(a, b, ) if a.dtype != torch.float64 else torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+        s2 = env.step(p2)[:4]
+        for a, b in zip(e2, s2):
+            assert torch.equal(torch.nan_to_num(a.double()), torch.nan_to_num(b.double()))
+        assert not torch.equal(base.q, q0) and int(base.steps.max()) > 0
