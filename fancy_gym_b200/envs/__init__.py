@@ -17,3 +17,25 @@ register(id='fancy/HoleReacher-v0', entry_point=HoleReacherEnv, mp_wrapper=MPWra
          max_episode_steps=200,
          kwargs={"n_links": 5, "random_start": True, "allow_self_collision": False, "allow_wall_collision": False,
                  "hole_width": None, "hole_depth": 1, "hole_x": None, "collision_penalty": 100})
+
+
+def _register_with_gymnasium():
+    """When gymnasium is installed, the same ids are also registered there (`gymnasium.make('fancy_ProMP/HoleReacher-v0',
+    num_envs=..., device=...)` then returns the batched black-box env of this package).  gymnasium is not a dependency."""
+    try:
+        import gymnasium
+    except Exception:       # noqa: BLE001
+        return False
+    from ..utils.gym_compat import registry as own
+    for env_id, spec in own.items():
+        if env_id in gymnasium.registry:
+            continue
+        try:
+            gymnasium.register(id=env_id, entry_point=spec.entry_point, max_episode_steps=None, kwargs=dict(spec.kwargs),
+                               disable_env_checker=True, order_enforce=False)
+        except Exception:   # noqa: BLE001
+            pass
+    return True
+
+
+_register_with_gymnasium()
