@@ -130,14 +130,11 @@ class BlackBoxWrapper(Wrapper):
         """next result set.  Envs whose episode ended in an earlier call are skipped by the kernel, so while several plans
         share one episode (replanning / sub-trajectories) their last observation and infos are carried over; the "unbounded"
         HoleReacher reward keeps per-episode state in info[:, 2:4] (fg_rollout_io.info)."""
-        prev_info, prev_obs = self._info, self._obs
+        self._prev_info, self._prev_obs = self._info, self._obs
         self._out_i ^= 1
         self._bind_outputs()
-        if self.do_replanning or self.learn_sub_trajectories:
-            self._obs.copy_(prev_obs)
-            self._info.copy_(prev_info)
-        elif getattr(self._base, "rew_fct", None) == "unbounded":
-            self._info[:, 2:4] = prev_info[:, 2:4]
+        if getattr(self._base, "rew_fct", None) == "unbounded":
+            self._info[:, 2:4] = self._prev_info[:, 2:4]
 
     # ---- spaces (black_box_wrapper.py:122-148) --------------------------------------------------
     def _get_traj_gen_action_space(self):
@@ -320,6 +317,8 @@ class BlackBoxWrapper(Wrapper):
         io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
         io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
         io.flag_bytes = self._flag_bytes[0].data_ptr()
+        if self.do_replanning or self.learn_sub_trajectories:      # frozen envs keep reporting their last observation / infos
+            io.prev_obs, io.prev_info = self._prev_obs.data_ptr(), self._prev_info.data_ptr()
         if dbg is not None:
             io.dbg_rewards = dbg["rewards"].data_ptr()
             if "actions" in dbg:

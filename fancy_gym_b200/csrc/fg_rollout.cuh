@@ -96,6 +96,10 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     io.flags[b] = 0;
     if (io.flag_bytes)
       for (int i = 0; i < 4; ++i) io.flag_bytes[i * B + b] = 0;
+    if (io.prev_obs)
+      for (int j = 0; j < c.n_obs_out; ++j) io.obs[b * c.n_obs_out + j] = io.prev_obs[b * c.n_obs_out + j];
+    if (io.prev_info)
+      for (int j = 0; j < 4; ++j) io.info[b * 4 + j] = io.prev_info[b * 4 + j];
     return;
   }
 

@@ -155,6 +155,8 @@ typedef struct fg_rollout_io {
   /* optional unpacked copies of the flag bits, one byte (0 / 1) per env each, or NULL: what step() returns as
    * terminated / truncated and infos['is_success'] / ['is_collided'] without any post-processing kernel */
   uint8_t* flag_bytes;     /* [4, B]: rows terminated, truncated, success, collided */
+  const float* prev_obs;   /* [B, n_obs_out] or NULL: observation / info rows reported for envs that are skipped because their */
+  const double* prev_info; /* [B, 4] or NULL      episode ended in an earlier call (they keep reporting their last values)   */
   int32_t keep_state;      /* 1: q / v / steps / done are read but NOT written back: the batch can be evaluated again from the
                               same start state with other parameters (population-based search on one context) */
 } fg_rollout_io;
