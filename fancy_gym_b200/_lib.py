@@ -73,6 +73,8 @@ class FgPhaseBasis(C.Structure):
         ("struct_size", C.c_uint32), ("phase_kind", C.c_int32), ("alpha_phase", C.c_double),
         ("n_basis_total", C.c_int32), ("first_learnable", C.c_int32),
         ("centers", C.c_double * 16), ("bandwidth", C.c_double * 16),
+        ("pc_pos", C.c_void_p), ("pc_vel", C.c_void_p), ("pc_y", C.c_void_p), ("n_pc", C.c_int32),
+        ("scaled_dt", C.c_float), ("init_time", C.c_float), ("scale", C.c_double * 17),
     ]
 
 

@@ -290,8 +290,7 @@ class BlackBoxWrapper(Wrapper):
         base = self._base
         B = self.num_envs
         T = self.traj_gen.n_steps
-        pg = self.traj_gen.phase_gn
-        per_env_phase = not (pg.uniform() or (self.traj_gen.mp_kind == _lib.MP_PRODMP and pg.collapse_if_equal()))
+        per_env_phase = not self.traj_gen.phase_gn.uniform()
         if per_env_phase:
             # learned tau / delay differ per env: fg_trajgen_phase evaluates the basis per env, the fused rollout then
             # tracks that trajectory from HBM (8 KB per env, far below its compute time)

@@ -216,12 +216,15 @@ fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const f
   if (!h || !pb || !times || !tau || !delay || !params || !pos_out || !vel_out)
     return fail(FG_ERR_INVALID, "fg_trajgen_phase: null argument");
   if (pb->struct_size != sizeof(fg_phase_basis)) return fail(FG_ERR_INVALID, "fg_trajgen_phase: struct_size mismatch (ABI)");
-  if (h->cfg.mp_kind != FG_MP_PROMP && h->cfg.mp_kind != FG_MP_DMP)
-    return fail(FG_ERR_UNSUPPORTED, "fg_trajgen_phase: per-env tau / delay is implemented for ProMP and DMP "
-                                    "(ProDMP's pre-integrated bases depend on tau)");
-  if (h->cfg.mp_kind == FG_MP_DMP && (!bc_pos || !bc_vel)) return fail(FG_ERR_INVALID, "fg_trajgen_phase: DMP needs boundary conditions");
-  if (pb->n_basis_total < 1 || pb->n_basis_total > 16 || pb->first_learnable < 0 ||
-      pb->first_learnable + h->cfg.n_basis > pb->n_basis_total)
+  if (h->cfg.mp_kind == FG_MP_TRAJ) return fail(FG_ERR_INVALID, "fg_trajgen_phase: handle has no trajectory generator");
+  if (h->cfg.mp_kind != FG_MP_PROMP && (!bc_pos || !bc_vel))
+    return fail(FG_ERR_INVALID, "fg_trajgen_phase: DMP / ProDMP need boundary conditions");
+  if (h->cfg.mp_kind == FG_MP_PRODMP && (!pb->pc_pos || !pb->pc_vel || !pb->pc_y || pb->n_pc < 2 || !(pb->scaled_dt > 0.f)))
+    return fail(FG_ERR_INVALID, "fg_trajgen_phase: ProDMP needs the pre-integrated basis tables");
+  if (h->cfg.n_basis + 1 > 17) return fail(FG_ERR_UNSUPPORTED, "fg_trajgen_phase: at most 16 basis functions");
+  if (h->cfg.mp_kind != FG_MP_PRODMP &&
+      (pb->n_basis_total < 1 || pb->n_basis_total > 16 || pb->first_learnable < 0 ||
+       pb->first_learnable + h->cfg.n_basis > pb->n_basis_total))
     return fail(FG_ERR_INVALID, "fg_trajgen_phase: basis counts inconsistent (total %d, first %d, weighted %d)",
                 pb->n_basis_total, pb->first_learnable, h->cfg.n_basis);
   if (B < 0) return fail(FG_ERR_INVALID, "fg_trajgen_phase: negative batch");
@@ -234,6 +237,9 @@ fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const f
   a.wscale = h->cfg.weights_scale; a.gscale = h->cfg.goal_scale; a.alpha = h->cfg.dmp_alpha; a.beta = h->cfg.dmp_alpha / 4.0f;
   a.times = times; a.dts = h->d_tab_b; a.tau = tau; a.delay = delay; a.params = params; a.bc_pos = bc_pos; a.bc_vel = bc_vel;
   a.pos = pos_out; a.vel = vel_out;
+  a.pc_pos = pb->pc_pos; a.pc_vel = pb->pc_vel; a.pc_y = pb->pc_y; a.n_pc = pb->n_pc; a.rel_goal = h->cfg.relative_goal;
+  a.scaled_dt = pb->scaled_dt; a.init_time = pb->init_time;
+  for (int k = 0; k < 17; ++k) a.scale[k] = pb->scale[k];
   int prev = 0;
   FG_CUDA(cudaGetDevice(&prev));
   if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));

@@ -48,6 +48,13 @@ struct PhaseArgs {
   const float* bc_vel;
   float* pos;                       // [B, T, N]
   float* vel;
+  // ProDMP: pre-integrated bases (float64, device), index rounding step, boundary time, parameter scales
+  const double* pc_pos;
+  const double* pc_vel;
+  const double* pc_y;
+  int n_pc, rel_goal;
+  float scaled_dt, init_time;
+  double scale[17];
 };
 
 cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t stream, int max_smem_optin, const char** why);

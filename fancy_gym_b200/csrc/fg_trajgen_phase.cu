@@ -40,9 +40,54 @@ __global__ void k_trajgen_phase(const __grid_constant__ PhaseArgs a) {
   for (int i = threadIdx.x; i < N * KP; i += blockDim.x) {
     float p = a.params[b * N * KP + i];
     if (a.mp_kind == FG_MP_DMP) p = __fmul_rn(p, (i % KP < K) ? a.wscale : a.gscale);
+    if (a.mp_kind == FG_MP_PRODMP && a.rel_goal && (i % KP) == K) p = __fadd_rn(p, a.bc_pos[b * N + i / KP]);
     s_w[i] = p;
   }
   __syncthreads();
+  if (a.mp_kind == FG_MP_PRODMP) {
+    // ProDMP (App. B.7): per env only the LOOKUP into the pre-integrated bases changes with tau / delay.  Indices are
+    // rounded in float32 like the library, the blend with the boundary condition is float64 rounded once to float32 —
+    // the arithmetic of the host-built shared tables (fancy_gym_b200/mp/mp.py ProDMP.tables).
+    auto index_of = [&](float t32) {
+      const float z = fmaxf(__fdiv_rn(__fsub_rn(t32, delay), tau), 0.f);
+      const int i = (int)rintf(__fdiv_rn(z, a.scaled_dt));
+      return min(max(i, 0), a.n_pc - 1);
+    };
+    const int KG = K + 1;
+    const int ib = index_of(a.init_time);
+    const double y1b = a.pc_y[ib * 4], y2b = a.pc_y[ib * 4 + 1], dy1b = a.pc_y[ib * 4 + 2], dy2b = a.pc_y[ib * 4 + 3];
+    const double det = y1b * dy2b - y2b * dy1b;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const int ix = index_of(a.times[t]);
+      const double y1 = a.pc_y[ix * 4], y2 = a.pc_y[ix * 4 + 1], dy1 = a.pc_y[ix * 4 + 2], dy2 = a.pc_y[ix * 4 + 3];
+      const double xi1 = dy2b / det * y1 - dy1b / det * y2, xi2 = y1b / det * y2 - y2b / det * y1;
+      const double xi3 = dy2b / det * dy1 - dy1b / det * dy2, xi4 = y1b / det * dy2 - y2b / det * dy1;
+      float hp[17], hv[17];
+      for (int k = 0; k < KG; ++k) {
+        hp[k] = (float)((a.pc_pos[ix * KG + k] - xi1 * a.pc_pos[ib * KG + k] - xi2 * a.pc_vel[ib * KG + k]) * a.scale[k]);
+        hv[k] = (float)((a.pc_vel[ix * KG + k] - xi3 * a.pc_pos[ib * KG + k] - xi4 * a.pc_vel[ib * KG + k]) * a.scale[k]);
+      }
+      const float x1 = (float)xi1, x2 = (float)xi2, x3 = (float)xi3, x4 = (float)xi4;
+      for (int d = 0; d < N; ++d) {
+        const float yb = a.bc_pos[b * N + d], vb = __fmul_rn(a.bc_vel[b * N + d], tau);
+        float ap = fmaf(x2, vb, fmaf(x1, yb, 0.f)), av = fmaf(x4, vb, fmaf(x3, yb, 0.f));     // table columns 0, 1
+        for (int k = 0; k < KG; ++k) {
+          ap = fmaf(hp[k], s_w[d * KP + k], ap);
+          av = fmaf(hv[k], s_w[d * KP + k], av);
+        }
+        s_pos[t * N + d] = ap;
+        s_vel[t * N + d] = __fdiv_rn(av, tau);
+      }
+    }
+    __syncthreads();
+    float* gp = a.pos + b * T * N;
+    float* gv = a.vel + b * T * N;
+    for (int i = threadIdx.x; i < T * N; i += blockDim.x) {
+      gp[i] = s_pos[i];
+      gv[i] = s_vel[i];
+    }
+    return;
+  }
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const float un = __fdiv_rn(__fsub_rn(a.times[t], delay), tau);       // float32 elementwise ops of the library
     const float z = fminf(fmaxf(un, 0.f), 1.f);

@@ -56,6 +56,7 @@ class MPInterface:
         self.init_vel = None
         self.params = None
         self._handles = {}
+        self._pc_dev = None
 
     # ---- attributes the reference reads -----------------------------------------------------
     @property
@@ -131,9 +132,6 @@ class MPInterface:
     def _phase_basis(self) -> "_lib.FgPhaseBasis":
         """constants of the phase / basis generators for the per-env-phase kernel (fg_phase_basis)"""
         bg, pg = self.basis_gn, self.phase_gn
-        if type(bg).__name__ == "ProDMPBasisGenerator" or self.mp_kind not in (_lib.MP_PROMP, _lib.MP_DMP):
-            raise NotImplementedError("per-env tau / delay is available for ProMP and DMP (ProDMP's pre-integrated bases "
-                                      "depend on tau); use one tau per batch")
         pb = _lib.FgPhaseBasis()
         pb.struct_size = C.sizeof(_lib.FgPhaseBasis)
         pb.phase_kind = 1 if pg.kind == "exp" else 0
@@ -143,6 +141,17 @@ class MPInterface:
             raise NotImplementedError("per-env phase: at most 16 basis functions")
         for k in range(bg.total_num_basis):
             pb.centers[k], pb.bandwidth[k] = float(bg.centers_p[k]), float(bg.bandwidth[k])
+        if self.mp_kind == _lib.MP_PRODMP:
+            # the pre-integrated bases depend on the construction-time tau only; per env only the lookup changes
+            if self._pc_dev is None:
+                self._pc_dev = tuple(torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.device)
+                                     for x in (bg.pc_pos_basis, bg.pc_vel_basis, bg.pc_y))
+            pb.pc_pos, pb.pc_vel, pb.pc_y = (x.data_ptr() for x in self._pc_dev)
+            pb.n_pc = int(bg.pc_y.shape[0])
+            pb.scaled_dt = float(np.float32(np.float32(bg.dt) / np.float32(pg._tau0)))
+            pb.init_time = float(np.float32(self.init_time))
+            for k, v in enumerate(self.weights_goal_scale()):
+                pb.scale[k] = float(v)
         return pb
 
     # ---- stand-alone trajectory generation on the GPU (fg_trajgen) ------------------------------
@@ -193,7 +202,7 @@ class MPInterface:
             pos, vel = out
             assert pos.shape == (B, T, N) and vel.shape == (B, T, N) and pos.is_contiguous() and vel.is_contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        if self.phase_gn.uniform() or (self.mp_kind == _lib.MP_PRODMP and self.phase_gn.collapse_if_equal()):
+        if self.phase_gn.uniform():
             _lib.check(_lib.lib.fg_trajgen(self._trajgen_handle(), p.data_ptr(), bp.data_ptr() if bp is not None else None,
                                            bv.data_ptr() if bv is not None else None, pos.data_ptr(), vel.data_ptr(), B,
                                            C.c_void_p(stream)))

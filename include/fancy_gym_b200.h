@@ -237,11 +237,20 @@ typedef struct fg_phase_basis {
   int32_t first_learnable;
   double centers[16];          /* in phase space */
   double bandwidth[16];
+  /* ProDMP only: the pre-integrated bases on the scaled-time grid z_j = j * scaled_dt (mp_pytorch ProDMPBasisGenerator
+   * pre-compute; they depend on the construction-time tau only) — float64 DEVICE tables, rows = grid points */
+  const double* pc_pos;        /* [n_pc, n_basis + 1] position bases (weights..., goal) */
+  const double* pc_vel;        /* [n_pc, n_basis + 1] velocity bases */
+  const double* pc_y;          /* [n_pc, 4]  y1, y2, dy1, dy2 of the homogeneous solution */
+  int32_t n_pc;
+  float scaled_dt;             /* float32(dt) / float32(tau at construction): grid step the library rounds indices with */
+  float init_time;             /* boundary-condition time of this plan */
+  double scale[17];            /* weights_scale (x n_basis), goal_scale (x auto-scale factors) */
 } fg_phase_basis;
 
 /*
- * fg_trajgen with per-env tau / delay (ProMP and DMP): the basis is evaluated in the kernel instead of read from the
- * handle's shared tables.  times [T] float32 time grid and tau / delay [B] float32 are DEVICE pointers; params holds the
+ * fg_trajgen with per-env tau / delay: the basis is evaluated in the kernel (ProMP, DMP) or looked up per env in the
+ * pre-integrated tables (ProDMP) instead of read from the handle's shared per-time-point tables.  times [T] float32 time grid and tau / delay [B] float32 are DEVICE pointers; params holds the
  * MP parameters only (tau / delay already stripped).  The fused rollout consumes pos_out / vel_out through a FG_MP_TRAJ handle.
  */
 fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const float* times, const float* tau,

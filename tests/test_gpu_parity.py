@@ -294,12 +294,15 @@ def test_blackbox_reset_fast_path_matches_wrapper_chain():
                                           ("fancy_ProMP/HoleReacher-v0", dict(learn_delay=True)),
                                           ("fancy_DMP/ViaPointReacher-v0", dict(learn_tau=True)),
                                           ("fancy_DMP/HoleReacher-v0", dict(learn_tau=True, learn_delay=True)),
-                                          ("fancy_ProMP/SimpleReacher-v0", dict(learn_tau=True))],
-                         ids=["promp-tau-delay", "promp-delay", "dmp-tau", "dmp-tau-delay", "promp-pd-tau"])
+                                          ("fancy_ProMP/SimpleReacher-v0", dict(learn_tau=True)),
+                                          ("fancy_ProDMP/SimpleReacher-v0", dict(learn_tau=True)),
+                                          ("fancy_ProDMP/HoleReacher-v0", dict(learn_tau=True, learn_delay=True))],
+                         ids=["promp-tau-delay", "promp-delay", "dmp-tau", "dmp-tau-delay", "promp-pd-tau", "prodmp-tau",
+                              "prodmp-tau-delay"])
 def test_per_env_tau_delay_matches_oracle(env_id, phase):
     fancy_gym = _fg()
     B = 300 + 7
-    mp_type = "promp" if "ProMP" in env_id else "dmp"
+    mp_type = "promp" if "ProMP" in env_id else ("prodmp" if "ProDMP" in env_id else "dmp")
     base_phase = dict(RESOLVED_PHASE(env_id), **phase)
     env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override={"phase_generator_kwargs": base_phase})
     env.reset(seed=50)
@@ -308,7 +311,8 @@ def test_per_env_tau_delay_matches_oracle(env_id, phase):
     params = (0.4 * rng.standard_normal((B, n_params_of(env_id) + n_extra))).astype(np.float32)
     i = 0
     if phase.get("learn_tau"):
-        params[:, i] = rng.uniform(0.3, 2.5, B)          # partly outside tau_bound = [0.02, 2.0]: clipped like the reference
+        # partly outside tau_bound = [0.02, 2.0]: clipped like the reference (ProDMP pre-computes 6 tau: keep t / tau <= 6)
+        params[:, i] = rng.uniform(0.45 if mp_type == "prodmp" else 0.3, 2.5, B)
         i += 1
     if phase.get("learn_delay"):
         params[:, i] = rng.uniform(0.0, 0.6, B)
