@@ -45,7 +45,7 @@ class FgRolloutIO(C.Structure):
         ("cond_pos", C.c_void_p), ("cond_vel", C.c_void_p),
         ("use_cond", C.c_int32), ("write_cond", C.c_int32),
         ("ret", C.c_void_p), ("length", C.c_void_p), ("flags", C.c_void_p), ("obs", C.c_void_p), ("info", C.c_void_p),
-        ("dbg_actions", C.c_void_p), ("dbg_obs", C.c_void_p), ("dbg_rewards", C.c_void_p), ("flag_bytes", C.c_void_p), ("prev_obs", C.c_void_p), ("prev_info", C.c_void_p), ("keep_state", C.c_int32),
+        ("dbg_actions", C.c_void_p), ("dbg_obs", C.c_void_p), ("dbg_rewards", C.c_void_p), ("flag_bytes", C.c_void_p), ("seg_steps_env", C.c_void_p), ("prev_obs", C.c_void_p), ("prev_info", C.c_void_p), ("keep_state", C.c_int32),
     ]
 
 
@@ -75,6 +75,7 @@ class FgPhaseBasis(C.Structure):
         ("centers", C.c_double * 16), ("bandwidth", C.c_double * 16),
         ("pc_pos", C.c_void_p), ("pc_vel", C.c_void_p), ("pc_y", C.c_void_p), ("n_pc", C.c_int32),
         ("scaled_dt", C.c_float), ("init_time", C.c_float), ("scale", C.c_double * 17),
+        ("n_steps_env", C.c_void_p), ("times_table", C.c_void_p), ("times_stride", C.c_int32),
     ]
 
 

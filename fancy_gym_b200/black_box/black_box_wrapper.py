@@ -316,6 +316,8 @@ class BlackBoxWrapper(Wrapper):
         io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
         io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
         io.flag_bytes = self._flag_bytes[0].data_ptr()
+        if per_env_phase and self.traj_gen.n_steps_env is not None:      # ragged sub-trajectories: per-env plan lengths
+            io.seg_steps_env = self.traj_gen.n_steps_env.data_ptr()
         if self.do_replanning or self.learn_sub_trajectories:      # frozen envs keep reporting their last observation / infos
             io.prev_obs, io.prev_info = self._prev_obs.data_ptr(), self._prev_info.data_ptr()
         if dbg is not None:

@@ -240,6 +240,9 @@ fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const f
   a.pc_pos = pb->pc_pos; a.pc_vel = pb->pc_vel; a.pc_y = pb->pc_y; a.n_pc = pb->n_pc; a.rel_goal = h->cfg.relative_goal;
   a.scaled_dt = pb->scaled_dt; a.init_time = pb->init_time;
   for (int k = 0; k < 17; ++k) a.scale[k] = pb->scale[k];
+  if ((pb->n_steps_env != nullptr) != (pb->times_table != nullptr))
+    return fail(FG_ERR_INVALID, "fg_trajgen_phase: n_steps_env and times_table go together");
+  a.n_steps_env = pb->n_steps_env; a.times_table = pb->times_table; a.times_stride = pb->times_stride;
   int prev = 0;
   FG_CUDA(cudaGetDevice(&prev));
   if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));

@@ -55,6 +55,10 @@ struct PhaseArgs {
   int n_pc, rel_goal;
   float scaled_dt, init_time;
   double scale[17];
+  // ragged plans: per-env number of points and the table of time grids (one row per length), or null
+  const int* n_steps_env;
+  const float* times_table;
+  int times_stride;
 };
 
 cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t stream, int max_smem_optin, const char** why);

@@ -259,7 +259,8 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   float pos[N], vel[N];
   double info0 = 0, info1 = 0;
 
-  for (; t < seg_steps; ++t) {
+  const int my_steps = io.seg_steps_env ? min(seg_steps, io.seg_steps_env[b]) : seg_steps;      // ragged sub-trajectories
+  for (; t < my_steps; ++t) {
     // ------------------------------------------------------------------ desired pos / vel at point t
     if constexpr (MP == FG_MP_PROMP) {
 #pragma unroll

@@ -28,14 +28,17 @@ __device__ __forceinline__ double eval_basis(const PhaseArgs& a, float z, double
 
 __global__ void k_trajgen_phase(const __grid_constant__ PhaseArgs a) {
   extern __shared__ float sm[];
-  const int N = a.N, T = a.T, K = a.K;
+  const int N = a.N, TM = a.T, K = a.K;      // TM: rows of the output buffers (the longest plan)
   const int KP = (a.mp_kind == FG_MP_PROMP) ? K : K + 1;
-  float* s_pos = sm;                 // [T, N]
-  float* s_vel = s_pos + T * N;      // [T, N]
-  float* s_f = s_vel + T * N;        // DMP: forcing [T, N]
-  float* s_h = s_f + T * N;          // DMP: scaled-time increments [T]
-  float* s_w = s_h + T;              // [N, KP] this env's parameters
+  float* s_pos = sm;                 // [TM, N]
+  float* s_vel = s_pos + TM * N;     // [TM, N]
+  float* s_f = s_vel + TM * N;       // DMP: forcing [TM, N]
+  float* s_h = s_f + TM * N;         // DMP: scaled-time increments [TM]
+  float* s_w = s_h + TM;             // [N, KP] this env's parameters
   const long long b = blockIdx.x;
+  // ragged plans: this env's own number of points and its own time grid (rows beyond it are never read by the rollout)
+  const int T = a.n_steps_env ? min(max(a.n_steps_env[b], 2), TM) : TM;
+  const float* times = a.n_steps_env ? a.times_table + (long long)T * a.times_stride : a.times;
   const float tau = a.tau[b], delay = a.delay[b];
   for (int i = threadIdx.x; i < N * KP; i += blockDim.x) {
     float p = a.params[b * N * KP + i];
@@ -58,7 +61,7 @@ __global__ void k_trajgen_phase(const __grid_constant__ PhaseArgs a) {
     const double y1b = a.pc_y[ib * 4], y2b = a.pc_y[ib * 4 + 1], dy1b = a.pc_y[ib * 4 + 2], dy2b = a.pc_y[ib * 4 + 3];
     const double det = y1b * dy2b - y2b * dy1b;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
-      const int ix = index_of(a.times[t]);
+      const int ix = index_of(times[t]);
       const double y1 = a.pc_y[ix * 4], y2 = a.pc_y[ix * 4 + 1], dy1 = a.pc_y[ix * 4 + 2], dy2 = a.pc_y[ix * 4 + 3];
       const double xi1 = dy2b / det * y1 - dy1b / det * y2, xi2 = y1b / det * y2 - y2b / det * y1;
       const double xi3 = dy2b / det * dy1 - dy1b / det * dy2, xi4 = y1b / det * dy2 - y2b / det * dy1;
@@ -80,16 +83,17 @@ __global__ void k_trajgen_phase(const __grid_constant__ PhaseArgs a) {
       }
     }
     __syncthreads();
-    float* gp = a.pos + b * T * N;
-    float* gv = a.vel + b * T * N;
+    float* gp = a.pos + b * TM * N;
+    float* gv = a.vel + b * TM * N;
     for (int i = threadIdx.x; i < T * N; i += blockDim.x) {
       gp[i] = s_pos[i];
       gv[i] = s_vel[i];
     }
+    for (int i = T * N + threadIdx.x; i < TM * N; i += blockDim.x) gp[i] = gv[i] = 0.f;      // ragged: rows past this env's plan
     return;
   }
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float un = __fdiv_rn(__fsub_rn(a.times[t], delay), tau);       // float32 elementwise ops of the library
+    const float un = __fdiv_rn(__fsub_rn(times[t], delay), tau);         // float32 elementwise ops of the library
     const float z = fminf(fmaxf(un, 0.f), 1.f);
     double phi[16];
     const double x = eval_basis(a, z, phi);
@@ -113,7 +117,8 @@ __global__ void k_trajgen_phase(const __grid_constant__ PhaseArgs a) {
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
       const int ts = (t < T - 1) ? t : T - 2;                 // vel[T-1] = vel[T-2]
       for (int d = 0; d < N; ++d)
-        s_vel[t * N + d] = (T > 1) ? __fdiv_rn(__fsub_rn(s_pos[(ts + 1) * N + d], s_pos[ts * N + d]), a.dts[ts]) : 0.f;
+        s_vel[t * N + d] = (T > 1) ? __fdiv_rn(__fsub_rn(s_pos[(ts + 1) * N + d], s_pos[ts * N + d]),
+                                               __fsub_rn(times[ts + 1], times[ts])) : 0.f;
     }
   } else {
     if (threadIdx.x < N) {          // serial semi-implicit Euler in scaled time, every op rounded separately
@@ -135,12 +140,13 @@ __global__ void k_trajgen_phase(const __grid_constant__ PhaseArgs a) {
     }
   }
   __syncthreads();
-  float* gp = a.pos + b * T * N;
-  float* gv = a.vel + b * T * N;
+  float* gp = a.pos + b * TM * N;
+  float* gv = a.vel + b * TM * N;
   for (int i = threadIdx.x; i < T * N; i += blockDim.x) {
     gp[i] = s_pos[i];
     gv[i] = s_vel[i];
   }
+  for (int i = T * N + threadIdx.x; i < TM * N; i += blockDim.x) gp[i] = gv[i] = 0.f;        // ragged: rows past this env's plan
 }
 
 cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t stream, int max_smem_optin, const char** why) {

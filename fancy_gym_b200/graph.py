@@ -61,3 +61,92 @@ class GraphedEpisode:
         if sync:
             torch.cuda.current_stream(self.env.device).synchronize()
         return self.host_ret, self.host_len, self.host_terminated
+
+
+class EpisodePipeline:
+    """Double-buffered episode batches for throughput loops that can keep two populations in flight (the
+    step_async / step_wait pattern of vector envs): while the fused rollout of batch k runs, the parameters of batch
+    k + 1 cross PCIe on a copy stream and the results of batch k - 1 return on another, so a step costs
+    max(rollout, H2D, D2H) instead of their sum.
+
+        pipe = EpisodePipeline(env)                       # env from fancy_gym_b200.make(...), reset(seed=...) once
+        pipe.host_params[0][:] = population_0; pipe.submit(0)
+        pipe.host_params[1][:] = population_1; pipe.submit(1)
+        ret, length, terminated = pipe.wait(0)            # pinned host tensors of slot 0, valid until its next submit()
+        pipe.host_params[0][:] = population_2; pipe.submit(0) ...
+
+    Every submit() is reset (next context of every env's stream) -> H2D -> env.step() -> D2H, through the same public
+    calls as the synchronous path; only the streams differ.  Episodes run in submission order on one compute stream (the
+    envs' context streams advance exactly as with sequential reset() / step() calls).  Like GraphedEpisode: one plan per
+    episode only."""
+
+    SLOTS = 2      # == the wrapper's alternating result sets: the results of batch k stay valid while batch k + 1 runs
+
+    def __init__(self, env):
+        if env.do_replanning or env.learn_sub_trajectories:
+            raise NotImplementedError("EpisodePipeline runs one plan per episode")
+        if not env._fast_reset:
+            raise NotImplementedError("EpisodePipeline needs the device-side reset (context_sampler='device')")
+        self.env = env
+        dev = env.device
+        B, P = env.num_envs, env.action_space.shape[0]
+        n = self.SLOTS
+        self.host_params = [torch.zeros(B, P, dtype=torch.float32).pin_memory() for _ in range(n)]
+        self.host_ret = [torch.zeros(B, dtype=torch.float64).pin_memory() for _ in range(n)]
+        self.host_len = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(n)]
+        self.host_terminated = [torch.zeros(B, dtype=torch.bool).pin_memory() for _ in range(n)]
+        self._params = [torch.zeros(B, P, dtype=torch.float32, device=dev) for _ in range(n)]
+        self._s_in, self._s_run, self._s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self._ev_in = [torch.cuda.Event() for _ in range(n)]          # parameters of the slot are on the device
+        self._ev_run = [torch.cuda.Event() for _ in range(n)]         # rollout of the slot finished
+        self._ev_out = [torch.cuda.Event() for _ in range(n)]         # results of the slot are on the host
+        self._next = 0
+        self._pending = [False] * n
+        if env.unwrapped._rng_state is None:
+            env.reset(seed=None)
+        for s in (self._s_in, self._s_run, self._s_out):
+            s.wait_stream(torch.cuda.current_stream(dev))
+
+    @property
+    def next_slot(self) -> int:
+        """the slot the next submit() must use (slots alternate)"""
+        return self._next
+
+    def submit(self, slot: int):
+        """enqueues one episode batch with the parameters in host_params[slot]; returns immediately"""
+        if slot != self._next:
+            raise ValueError(f"slots are used in turn: expected {self._next}, got {slot}")
+        if self._pending[slot]:
+            raise RuntimeError(f"slot {slot} still holds results that were not collected with wait()")
+        env = self.env
+        self._s_in.wait_event(self._ev_run[slot])          # the slot's device parameters are no longer being read
+        with torch.cuda.stream(self._s_in):
+            self._params[slot].copy_(self.host_params[slot], non_blocking=True)
+            self._ev_in[slot].record(self._s_in)
+        self._s_run.wait_event(self._ev_in[slot])
+        self._s_run.wait_event(self._ev_out[slot])         # the result set this step overwrites has been copied out
+        with torch.cuda.stream(self._s_run):
+            env.reset(seed=None, options={"as_numpy": False})
+            _obs, ret, terminated, _trunc, info = env.step(self._params[slot])
+            self._ev_run[slot].record(self._s_run)
+        self._s_out.wait_event(self._ev_run[slot])
+        with torch.cuda.stream(self._s_out):
+            self.host_ret[slot].copy_(ret, non_blocking=True)
+            self.host_len[slot].copy_(info["trajectory_length"], non_blocking=True)
+            self.host_terminated[slot].copy_(terminated, non_blocking=True)
+            self._ev_out[slot].record(self._s_out)
+        self._pending[slot] = True
+        self._next = (slot + 1) % self.SLOTS
+
+    def wait(self, slot: int):
+        """blocks until the results of the batch submitted in `slot` are in pinned host memory and returns them"""
+        if not self._pending[slot]:
+            raise RuntimeError(f"nothing was submitted in slot {slot}")
+        self._ev_out[slot].synchronize()
+        self._pending[slot] = False
+        return self.host_ret[slot], self.host_len[slot], self.host_terminated[slot]
+
+    def drain(self):
+        """waits for everything in flight (results stay readable)"""
+        for s in (self._s_in, self._s_run, self._s_out):
+            s.synchronize()

@@ -57,6 +57,7 @@ class MPInterface:
         self.params = None
         self._handles = {}
         self._pc_dev = None
+        self.n_steps_env = None
 
     # ---- attributes the reference reads -----------------------------------------------------
     @property
@@ -101,18 +102,31 @@ class MPInterface:
 
     def set_duration(self, duration, dt):
         self.dt = float(dt)
+        self.n_steps_env = None
         if duration is None:     # learn_sub_trajectories: trajectory length follows the learned tau
             if not self.phase_gn.collapse_if_equal():
-                # one plan length per launch: the batch must agree on round(tau / dt) (this reads tau back to the host)
-                tau = self.phase_gn.tau.detach().cpu()
-                steps = torch.round(tau / dt)
-                if not bool((steps == steps.flatten()[0]).all()):
-                    raise NotImplementedError("sub-trajectory length must be the same for all envs of a batch")
-                tau0 = float(tau.flatten()[0])
+                # the envs of the batch chose different taus: ragged plans.  Env b plans round(tau_b / dt) points; buffers and
+                # launches are sized for the longest admissible plan (tau_bound), the lengths stay on the device.
+                t_max = int(np.round(float(self.phase_gn.tau_bound[1]) / dt))
+                tau = self.phase_gn.tau.to(self.device, torch.float64)
+                self.n_steps_env = torch.round(tau / dt).clamp_(2, t_max).to(torch.int32).contiguous()
+                duration = float(t_max * dt)
             else:
-                tau0 = self.phase_gn.scalar_tau()
-            duration = float(np.round(tau0 / dt) * dt)
+                duration = float(np.round(self.phase_gn.scalar_tau() / dt) * dt)
         self.duration = float(duration)
+
+    def _times_table(self):
+        """[T_max + 1, T_max] float32: row n is the library's time grid of an n-point plan (torch.linspace on the host, so
+        the rounding pattern is the library's), zero padded — the per-env grids of ragged plans are looked up here"""
+        key = (self.n_steps, self.dt, float(np.float32(self.init_time)))
+        if getattr(self, "_tt_key", None) != key:
+            t_max = self.n_steps
+            tab = np.zeros((t_max + 1, t_max), dtype=np.float32)
+            for n in range(1, t_max + 1):
+                tab[n, :n] = time_grid32(float(n * self.dt), self.dt, self.init_time)
+            self._tt = torch.as_tensor(tab, device=self.device)
+            self._tt_key = key
+        return self._tt
 
     @property
     def n_steps(self) -> int:
@@ -152,6 +166,9 @@ class MPInterface:
             pb.init_time = float(np.float32(self.init_time))
             for k, v in enumerate(self.weights_goal_scale()):
                 pb.scale[k] = float(v)
+        if self.n_steps_env is not None:
+            tt = self._times_table()
+            pb.n_steps_env, pb.times_table, pb.times_stride = self.n_steps_env.data_ptr(), tt.data_ptr(), tt.shape[1]
         return pb
 
     # ---- stand-alone trajectory generation on the GPU (fg_trajgen) ------------------------------

@@ -155,6 +155,8 @@ typedef struct fg_rollout_io {
   /* optional unpacked copies of the flag bits, one byte (0 / 1) per env each, or NULL: what step() returns as
    * terminated / truncated and infos['is_success'] / ['is_collided'] without any post-processing kernel */
   uint8_t* flag_bytes;     /* [4, B]: rows terminated, truncated, success, collided */
+  const int32_t* seg_steps_env; /* [B] or NULL: per-env bound on the steps of this segment (ragged sub-trajectories); the
+                                   scalar seg_steps argument still bounds all of them */
   const float* prev_obs;   /* [B, n_obs_out] or NULL: observation / info rows reported for envs that are skipped because their */
   const double* prev_info; /* [B, 4] or NULL      episode ended in an earlier call (they keep reporting their last values)   */
   int32_t keep_state;      /* 1: q / v / steps / done are read but NOT written back: the batch can be evaluated again from the
@@ -246,6 +248,12 @@ typedef struct fg_phase_basis {
   float scaled_dt;             /* float32(dt) / float32(tau at construction): grid step the library rounds indices with */
   float init_time;             /* boundary-condition time of this plan */
   double scale[17];            /* weights_scale (x n_basis), goal_scale (x auto-scale factors) */
+  /* ragged plans (learn_sub_trajectories with a different tau per env): env b plans n_steps_env[b] <= n_steps points on
+   * the time grid times_table[n_steps_env[b] * times_stride + i] (float32 DEVICE table with one row per possible length,
+   * built by the caller with the library's own linspace); NULL / NULL: every env uses `times` and n_steps points */
+  const int32_t* n_steps_env;
+  const float* times_table;
+  int32_t times_stride;
 } fg_phase_basis;
 
 /*

@@ -199,6 +199,9 @@ class BlackBoxOracle:
                                                    t + 1 + self.current_traj_steps)) \
                 and self.plan_steps < self.max_planning_times
             stop = run & (term | trunc | replan)
+            n_valid = getattr(self.traj_gen, "n_valid", None)
+            if n_valid is not None:          # ragged sub-trajectories: an env's plan ends after its own number of steps
+                stop = stop | (run & (t + 1 >= n_valid))
             if self.condition_on_desired and stop.any():
                 if new_cond_pos is None:
                     new_cond_pos = np.array(env.current_pos, dtype=pos.dtype)

@@ -388,14 +388,24 @@ class MPBase:
         self.init_vel = np.asarray(init_vel, dtype=self.dtype)
 
     def set_duration(self, duration, dt):
-        """App. B.1: T = round(duration/dt) points init_time + dt*(1..T); duration None -> tau."""
+        """App. B.1: T = round(duration/dt) points init_time + dt*(1..T); duration None -> round(tau/dt)*dt.
+        With per-env tau (a batch whose envs chose different sub-trajectory lengths) every env gets its own grid; the
+        rows are padded to the longest one by repeating the last time point and `n_valid[b]` holds the true length."""
         self.dt = float(dt)
+        self.n_valid = None
+        t0 = 0.0 if self.init_time is None else self.init_time
         if duration is None:
             tau = np.asarray(self.phase_gn.tau, dtype=F64)
-            assert tau.ndim == 0 or np.all(tau == tau.flat[0]), "sub-trajectory length must be uniform in a batch"
+            if tau.ndim and not np.all(tau == tau.flat[0]):
+                steps = np.round(tau / dt).astype(np.int64)
+                rows = [time_grid(float(n * dt), dt, t0, self.mode) for n in steps]
+                tmax = int(steps.max())
+                self.times = np.stack([np.concatenate([r, np.full(tmax - len(r), r[-1], dtype=r.dtype)]) for r in rows])
+                self.n_valid = steps
+                self.duration = float(tmax * dt)
+                return
             duration = float(np.round(float(tau.flat[0]) / dt) * dt)
         self.duration = duration
-        t0 = 0.0 if self.init_time is None else self.init_time
         self.times = time_grid(duration, dt, t0, self.mode)
 
     def _phase_times(self):
@@ -435,8 +445,12 @@ class ProMP(MPBase):
         pos = self.get_traj_pos()
         vel = np.zeros_like(pos)
         dts = np.diff(self.times, axis=-1)
-        vel[..., :-1, :] = np.diff(pos, axis=-2) / dts[..., None]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            vel[..., :-1, :] = np.diff(pos, axis=-2) / dts[..., None]
         vel[..., -1, :] = vel[..., -2, :]
+        if getattr(self, "n_valid", None) is not None:        # ragged batch: the last VALID row duplicates its predecessor
+            for b, n in enumerate(self.n_valid):
+                vel[b, n - 1] = vel[b, n - 2]
         return vel
 
 

@@ -287,3 +287,38 @@ def test_graphed_episode_replays_the_eager_episode(fg):
         assert torch.equal(runner.host_obs, obs0.cpu())
         assert torch.equal(ret, e_ret.cpu()) and torch.equal(length, e_info["trajectory_length"].cpu())
         assert torch.equal(term, e_term.cpu())
+
+
+def test_episode_pipeline_equals_sequential_steps(fg):
+    """EpisodePipeline (two batches in flight, H2D / rollout / D2H on their own streams) returns, batch for batch, what
+    sequential reset() / step() calls return — including each env's context stream advancing once per batch"""
+    import torch
+    B = 4096
+    seq = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
+    piped = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
+    seq.reset(seed=3)
+    piped.reset(seed=3)
+    pipe = fg.EpisodePipeline(piped)
+    gen = torch.Generator().manual_seed(1)
+    pops = [0.5 * torch.randn(B, 25, generator=gen) for _ in range(7)]
+    want = []
+    for p in pops:
+        seq.reset(seed=None)
+        _, ret, term, _, info = seq.step(p.to(DEV))
+        want.append((ret.cpu(), info["trajectory_length"].cpu(), term.cpu()))
+    got = [None] * len(pops)
+    for i, p in enumerate(pops):
+        s = i % pipe.SLOTS
+        if i >= pipe.SLOTS:
+            got[i - pipe.SLOTS] = tuple(x.clone() for x in pipe.wait(s))
+        pipe.host_params[s].copy_(p)
+        pipe.submit(s)
+    for i in range(len(pops) - pipe.SLOTS, len(pops)):
+        got[i] = tuple(x.clone() for x in pipe.wait(i % pipe.SLOTS))
+    for w, g in zip(want, got):
+        assert all(torch.equal(a, b) for a, b in zip(w, g))
+    assert len({float(w[0].sum()) for w in want}) == len(pops)          # the batches differ: nothing was compared with itself
+    with pytest.raises(ValueError):
+        pipe.submit(1 - pipe.next_slot)
+    with pytest.raises(RuntimeError):
+        pipe.wait(0)

@@ -489,6 +489,56 @@ def test_sub_trajectory_sequencing_matches_oracle(env_id):
     assert (total <= 200).all() and (total[~ever_terminated] == 200).all()
 
 
+@pytest.mark.parametrize("env_id", ["fancy_ProDMP/SimpleReacher-v0", "fancy_ProMP/HoleReacher-v0", "fancy_DMP/ViaPointReacher-v0"])
+def test_ragged_sub_trajectories_match_oracle(env_id):
+    """learn_sub_trajectories where every env of the batch learns its OWN tau: env b plans round(tau_b / dt) points on its
+    own time grid (fg_phase_basis.n_steps_env / times_table) and the fused rollout stops it after that many steps
+    (fg_rollout_io.seg_steps_env).  The oracle's batched version is pinned to its scalar loop in
+    tests/test_oracle_golden.py::test_ragged_sub_trajectories_equal_the_scalar_loop."""
+    fancy_gym = _fg()
+    B = 193
+    env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override={"black_box_kwargs": {"learn_sub_trajectories": True}})
+    orc = make_oracle(env_id, mode="mirror", learn_sub_trajectories=True)
+    env.reset(seed=5)
+    orc.reset(seeds=5 + np.arange(B))
+    rng = np.random.default_rng(11)
+    P = env.action_space.shape[0]
+    total = np.zeros(B, dtype=np.int64)
+    live = np.ones(B, bool)
+    for k in range(5):
+        params = (0.4 * rng.standard_normal((B, P))).astype(np.float32)
+        params[:, 0] = rng.uniform(0.05, 0.9, size=B).astype(np.float32)
+        if k == 0:      # the stand-alone trajectory of a ragged batch: bit-exact on every env's own rows, zero beyond
+            pos, vel = env.get_trajectory(torch.as_tensor(params, device="cuda:0"))
+            o_pos, o_vel = orc.get_trajectory(params)
+            n_valid = np.asarray(orc.traj_gen.n_valid)
+            assert pos.shape[1] == env.traj_gen.n_steps >= n_valid.max()
+            pos, vel = pos.cpu().numpy(), vel.cpu().numpy()
+            for b in range(B):
+                n = n_valid[b]
+                assert np.array_equal(pos[b, :n], o_pos[b, :n]) and np.array_equal(vel[b, :n], o_vel[b, :n]), b
+                assert not pos[b, n:].any() and not vel[b, n:].any()
+        o_obs, o_ret, o_te, o_tr, o_info = orc.step(params)
+        obs, ret, te, tr, info = env.step(params)
+        tie = o_info["min_margin"] < TIE_EPS
+        agree = (info["trajectory_length"] == o_info["trajectory_length"]) & (te == o_te) & (tr == o_tr)
+        assert (agree | tie).all(), (k, int((~(agree | tie)).sum()))
+        if tie.any() and not agree.all():
+            pytest.skip("a boundary tie resolved differently: the two sides diverge from here on")
+        fin = np.isfinite(o_ret)
+        assert rel_err(ret[fin], o_ret[fin]).max() < 1e-5 if fin.any() else True
+        assert (np.abs(obs - o_obs) <= 2e-5 * np.maximum(1.0, np.abs(o_obs))).all(), k
+        ran_through = live & ~(te | tr)
+        want = np.round(params[:, 0].astype(np.float64) / 0.01).astype(np.int64)
+        assert (info["trajectory_length"][ran_through] == want[ran_through]).all()
+        if k == 0:
+            assert len(set(info["trajectory_length"][ran_through].tolist())) > 10        # the batch really is ragged
+        assert (info["trajectory_length"][~live] == 0).all()
+        live &= ~(te | tr)
+        total += info["trajectory_length"]
+    assert (total <= 200).all()
+
+
 def test_env_on_a_non_current_device():
     """every entry point selects the device of its buffers itself (one process driving cuda:1 while cuda:0 is current)"""
     if torch.cuda.device_count() < 2:

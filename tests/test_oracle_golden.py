@@ -94,3 +94,32 @@ def test_blackbox_loop_matches_reference_wrapper(case, golden_dir):
             assert close64(ret[b], g["ret"][b, i])
             assert te[b] == g["terminated"][b, i] and tr[b] == g["truncated"][b, i]
             assert np.array_equal(ob[b], g["obs"][b, i])
+
+
+@pytest.mark.parametrize("env_id", ["fancy_ProMP/HoleReacher-v0", "fancy_DMP/ViaPointReacher-v0", "fancy_ProDMP/SimpleReacher-v0"])
+def test_ragged_sub_trajectories_equal_the_scalar_loop(env_id):
+    """learn_sub_trajectories with a DIFFERENT learned tau per env of a batch: the batched oracle (per-env time grids,
+    per-env plan lengths) must be what the reference does env by env (black_box_wrapper.py:96-120,150-217 on one env each,
+    here the oracle at B = 1, which the golden black-box cases pin)."""
+    B = 6
+    orc = make_oracle(env_id, mode="mirror", learn_sub_trajectories=True)
+    orc.reset(seeds=3 + np.arange(B))
+    singles = []
+    for b in range(B):
+        o = make_oracle(env_id, mode="mirror", learn_sub_trajectories=True)
+        o.reset(seeds=[3 + b])
+        singles.append(o)
+    rng = np.random.default_rng(0)
+    P = orc.traj_gen.num_params
+    total = np.zeros(B, dtype=np.int64)
+    for k in range(4):
+        params = (0.4 * rng.standard_normal((B, P))).astype(np.float32)
+        params[:, 0] = rng.uniform(0.1, 1.2, size=B).astype(np.float32)
+        obs, ret, te, tr, info = orc.step(params)
+        for b in range(B):
+            o_obs, o_ret, o_te, o_tr, o_info = singles[b].step(params[b:b + 1])
+            assert info["trajectory_length"][b] == o_info["trajectory_length"][0]
+            assert np.array_equal(obs[b], o_obs[0]) and np.array_equal(ret[b:b + 1], o_ret, equal_nan=True)
+            assert te[b] == o_te[0] and tr[b] == o_tr[0]
+        total += info["trajectory_length"]
+    assert (total <= 200).all()
