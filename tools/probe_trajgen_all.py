@@ -34,3 +34,4 @@ run("fancy_DMP/ViaPointReacher-v0", "DMP (k_trajgen_dmp)")
 run("fancy_ProDMP/SimpleReacher-v0", "ProDMP dof 2 (k_trajgen_closed)")
 run("fancy_ProMP/HoleReacher-v0", "ProMP per-env tau (k_trajgen_phase)", dict(phase_generator_type="linear", learn_tau=True))
 run("fancy_DMP/ViaPointReacher-v0", "DMP per-env tau (k_trajgen_phase)", dict(phase_generator_type="exp", alpha_phase=2, learn_tau=True))
+run("fancy_ProDMP/HoleReacher-v0", "ProDMP per-env tau (k_trajgen_phase)", dict(learn_tau=True))
