@@ -274,13 +274,27 @@ def main():
                                                done=torch.zeros_like(base.done), ctx=base.ctx.clone())))
 
     from fancy_gym_b200.dist import all_gather_result_blocks
-    gathered = torch.zeros(world * env._result_block.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = [torch.zeros(world * env._result_block.numel(), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    in_flight = [None]
+    n_gathers = [0]
 
     def gather_results():
         """returns / lengths / flags of every rank to every rank: ONE NCCL all-gather of the step's result block per step,
-        no packing kernels (fancy_gym_b200/dist)"""
+        no packing kernels (fancy_gym_b200/dist).  The exchange of step k runs on NCCL's stream while the rollout of step
+        k + 1 (which writes the wrapper's other result set) runs on ours; before step k + 1 starts ITS exchange the stream
+        waits for that of step k, so the rollout of step k + 2 never overwrites a block that is still being sent."""
         if world > 1:
-            all_gather_result_blocks(env._result_block, out=gathered)
+            if in_flight[0] is not None:
+                in_flight[0].wait()
+            in_flight[0] = all_gather_result_blocks(env._result_block, out=gathered[n_gathers[0] % 2], async_op=True)[1]
+            n_gathers[0] += 1
+            if os.environ.get("FG_BENCH_SYNC_GATHER"):      # (experiment switch: no overlap with the next rollout)
+                finish_gathers()
+
+    def finish_gathers():
+        if in_flight[0] is not None:
+            in_flight[0].wait()
+            in_flight[0] = None
 
     def step_device(s):
         env.launch(s["params"], state=s["state"], keep_state=True)
@@ -297,6 +311,7 @@ def main():
     for i in range(W):
         step_device(sets[i % n_sets])
         total_steps += env._len.sum()
+    finish_gathers()
     sync_all()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -315,6 +330,7 @@ def main():
             kev[i][1].record()
             gather_results()
             total_steps += env._len.sum()
+        finish_gathers()       # the last exchange is inside the timed region
         t_end.record()
         host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K     # host time to ISSUE one step (no sync inside)
         sync_all()
@@ -491,7 +507,7 @@ def main():
                                 envs_per_gpu=B, n_params=N_PARAMS, sigma=args.sigma, max_episode_steps=200,
                                 contexts="device sampler (numpy-exact PCG64 streams, fg_reset)", parallelism=f"env-shard x{world}",
                                 l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
-                                collective="all_gather(return,length,flags) per step" if world > 1 else "none"),
+                                collective="all_gather(return,length,flags) per step, overlapped with the next rollout" if world > 1 else "none"),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_sync=e2e_sync, e2e_graph=e2e_graph,
                     clocks=clk.summary(), gpu_launches=K)

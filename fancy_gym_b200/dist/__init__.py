@@ -104,13 +104,19 @@ def result_block_flag_bytes(block: torch.Tensor, num_envs: int):
     return fb[..., 0, :], fb[..., 1, :], fb[..., 2, :], fb[..., 3, :]
 
 
-def all_gather_result_blocks(block: torch.Tensor, out: Optional[torch.Tensor] = None, group=None):
+def all_gather_result_blocks(block: torch.Tensor, out: Optional[torch.Tensor] = None, group=None, async_op: bool = False):
     """ONE all-gather of every rank's result block -> [world, nbytes] (rank-major = global env order for even shards).
-    Identity ([1, nbytes] view) without a process group."""
+    Identity ([1, nbytes] view) without a process group.
+
+    async_op=True returns (gathered, work): the collective runs on NCCL's own stream behind everything enqueued so far,
+    and the CURRENT stream does not wait for it until work.wait() — so the next rollout (which writes the wrapper's other
+    result set) overlaps the exchange.  Call work.wait() before reading `gathered` and before the rollout after next
+    re-uses this step's result set."""
     if not (dist.is_available() and dist.is_initialized()):
-        return block[None]
+        return (block[None], None) if async_op else block[None]
     world = dist.get_world_size(group)
     if out is None:
         out = block.new_empty(world * block.numel())
-    dist.all_gather_into_tensor(out, block, group=group)
-    return out.view(world, block.numel())
+    work = dist.all_gather_into_tensor(out, block, group=group, async_op=async_op)
+    out = out.view(world, block.numel())
+    return (out, work) if async_op else out

@@ -84,6 +84,10 @@ def _block_worker(rank, world, port, B, q):
         flags.copy_(torch.as_tensor(rng.integers(0, 16, B).astype(np.uint8)))
         g_ret, g_len, g_flags = result_block_views(all_gather_result_blocks(block), B)
         ok = g_ret.shape == (world, B)
+        # the overlapped form: (gathered, work), readable after work.wait()
+        out2, work = all_gather_result_blocks(block, async_op=True)
+        work.wait()
+        ok &= bool(torch.equal(result_block_views(out2, B)[0], g_ret))
         for r in range(world):
             rr = np.random.default_rng(r)
             ok &= bool(np.array_equal(g_ret[r].numpy(), rr.standard_normal(B)))
