@@ -43,8 +43,10 @@ OPS_PER_ENV_STEP = 4356          # SURVEY.md §8d, HoleReacher/ProMP (FMA = 2, e
 TRAJ_BYTES_PER_ENV = 2 * 200 * 5 * 4 + N_PARAMS * 4   # fg_trajgen: pos + vel out, params in
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at
 # the same sizes (profiles/r1_rollout_ncu_summary.txt, profiles/r1_trajgen_ncu_summary.txt)
-NCU_TRAFFIC_ROLLOUT = 14_296_576 + 1_024
-NCU_TRAFFIC_TRAJGEN = 26_361_856 + 2_041_428_000
+NCU_TRAFFIC_ROLLOUT = 14_299_648 + 256
+NCU_TRAFFIC_TRAJGEN = 26_288_384 + 2_039_226_000
+NCU_WARP_INSTRUCTIONS_ROLLOUT = 199_586_881     # smsp__inst_executed.sum of the same capture
+NCU_PIPES_ROLLOUT = dict(issue_active=68.4, alu=46.3, fma=28.3, xu=24.3, fp64=11.0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -499,6 +501,14 @@ def main():
         cpu = ref.baseline()
         ref.close()
 
+    clocks = clk.summary()
+    if B == B_PER_GPU and clocks.get("sm_mhz"):
+        # what the machine actually executed: warp instructions of the committed ncu capture of this launch / live kernel time
+        # against the issue rate (4 schedulers x 1 instruction per clock per SM at the sampled SM clock); pipe shares: the capture's
+        roofline["executed"] = dict(warp_instructions_per_launch=NCU_WARP_INSTRUCTIONS_ROLLOUT,
+                                    issue_slot_frac=NCU_WARP_INSTRUCTIONS_ROLLOUT / (kernel_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sm_count * 4),
+                                    ncu_pct_of_peak_sustained_active=NCU_PIPES_ROLLOUT,
+                                    source="profiles/r1_rollout_ncu_summary.txt (ncu --set full of this launch)")
     if rank == 0:
         line = dict(metric="env-steps/sec (fancy_ProMP/HoleReacher-v0 MP black-box rollout)", value=value, unit="env-steps/s",
                     n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms_max / K, higher_is_better=True, scaling="weak",
@@ -510,7 +520,7 @@ def main():
                                 collective="all_gather(return,length,flags) per step, overlapped with the next rollout" if world > 1 else "none"),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_sync=e2e_sync, e2e_graph=e2e_graph,
-                    clocks=clk.summary(), gpu_launches=K)
+                    clocks=clocks, gpu_launches=K)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
