@@ -245,10 +245,18 @@ k_trajgen_closed(const __grid_constant__ DevCfg c, const float* __restrict__ par
 // DMP: the Euler recurrence is serial in time, so a lane owns one (env, dof) pair and a warp G = 32 / N envs.  The lanes
 // write their position / scaled velocity into a per-warp staging buffer, CH time points at a time, and every env's
 // [CH, N] blocks then leave the SM as TMA bulk stores (instead of 20-byte pieces scattered over G different lines per
-// store instruction); the recurrence of the next chunk overlaps the drain.
-constexpr int kDmpThreads = 128;
+// store instruction); the recurrence of the next chunk overlaps the drain.  Chunk size, measured at 262 144 envs x [200, 5]:
+// 8 points 0.771 ms, 12: 0.690, 16: 0.687, 20: 0.623, 40: 0.797, 100: 1.38, 200: 2.44 — the recurrence is a latency chain, so
+// resident warps (i.e. little staging memory per warp) matter more than large bulk copies.
+#ifndef FG_DMP_THREADS
+#define FG_DMP_THREADS 128
+#endif
+#ifndef FG_DMP_CHUNK
+#define FG_DMP_CHUNK 20
+#endif
+constexpr int kDmpThreads = FG_DMP_THREADS;
 constexpr int kDmpWarps = kDmpThreads / 32;
-constexpr int kDmpChunk = 40;            // time points staged at a time (a multiple of 4: 16-byte sized bulk copies)
+constexpr int kDmpChunk = FG_DMP_CHUNK;  // time points staged at a time (a multiple of 4: 16-byte sized bulk copies)
 
 template <int N>
 __global__ void __launch_bounds__(kDmpThreads)

@@ -152,9 +152,10 @@ __global__ void __launch_bounds__(256, FG_PHASE_MINB) k_trajgen_phase(const __gr
 // DMP with a per-env phase, second half: semi-implicit Euler in scaled time, every op rounded separately (the library's
 // recurrence).  A lane owns one (env, dof) pair and a warp G = 32 / N envs, like k_trajgen_dmp; the forcing term comes from
 // the velocity buffer (written by k_trajgen_phase) and is replaced in place, CH time points at a time through a per-warp
-// staging buffer and per-env TMA bulk stores.  A chunk's forcing values are read before its stores are issued, the
+// staging buffer and per-env TMA bulk stores (20 points: small stages keep ~44 warps resident per SM, which this
+// latency chain needs more than it needs large copies).  A chunk's forcing values are read before its stores are issued, the
 // scaled-time increments h = max((t_{i+1} - delay) / tau, 0) - max((t_i - delay) / tau, 0) are float32 ops off the chain.
-constexpr int kPhaseDmpChunk = 40;
+constexpr int kPhaseDmpChunk = 20;
 
 template <int N>
 __global__ void __launch_bounds__(kDmpThreads)
@@ -204,7 +205,7 @@ k_dmp_integrate_phase(const __grid_constant__ PhaseArgs a, const long long B) {
         ff[j] = gv[t * N + d];
         const float s_next = fmaxf(__fdiv_rn(__fsub_rn(times[t + 1], delay), tau), 0.f);
         hh[j] = __fsub_rn(s_next, s_prev);
-        if (c0 + r0 + j < T - 1) s_prev = s_next;
+        if (r0 + j < rows && c0 + r0 + j < T - 1) s_prev = s_next;      // (rows past the chunk belong to the next pass)
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
