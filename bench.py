@@ -259,7 +259,12 @@ def main():
     B = args.envs_per_gpu
     K, W = args.steps, args.warmup
 
-    env = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device")
+    # multi-GPU: the exchange of step k has to finish before the rollout of step k + RING re-uses its result block.  RING = 2
+    # (the wrapper's default) already hides the all-gather; deeper rings (4, 8: FG_BENCH_RESULT_RING) were measured at N = 4
+    # and change nothing (0.3367 ms per step each), i.e. the ranks are not waiting for each other's exchange
+    RING = int(os.environ.get("FG_BENCH_RESULT_RING", "2")) if world > 1 else 2
+    env = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device",
+                         mp_config_override={"black_box_kwargs": {"result_sets": RING}})
     base = env.unwrapped
     # rotating input sets so that every timed step reads inputs that are cold in the 126 MB L2
     set_bytes = B * (N_PARAMS * 4 + 5 * 8 * 2 + 4 * 8 + 5)
@@ -276,27 +281,26 @@ def main():
                                                done=torch.zeros_like(base.done), ctx=base.ctx.clone())))
 
     from fancy_gym_b200.dist import all_gather_result_blocks
-    gathered = [torch.zeros(world * env._result_block.numel(), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
-    in_flight = [None]
+    gathered = [torch.zeros(world * env._result_block.numel(), dtype=torch.uint8, device=dev) for _ in range(RING)] if world > 1 else None
+    in_flight = []
     n_gathers = [0]
 
     def gather_results():
         """returns / lengths / flags of every rank to every rank: ONE NCCL all-gather of the step's result block per step,
-        no packing kernels (fancy_gym_b200/dist).  The exchange of step k runs on NCCL's stream while the rollout of step
-        k + 1 (which writes the wrapper's other result set) runs on ours; before step k + 1 starts ITS exchange the stream
-        waits for that of step k, so the rollout of step k + 2 never overwrites a block that is still being sent."""
+        no packing kernels (fancy_gym_b200/dist).  The exchange of step k runs on NCCL's stream while the rollouts of the
+        next steps (which write the OTHER result sets of the wrapper's ring) run on ours; before step k starts ITS
+        exchange the stream waits for that of step k - (RING - 1), so no rollout overwrites a block that is still being sent."""
         if world > 1:
-            if in_flight[0] is not None:
-                in_flight[0].wait()
-            in_flight[0] = all_gather_result_blocks(env._result_block, out=gathered[n_gathers[0] % 2], async_op=True)[1]
+            while len(in_flight) > RING - 2:
+                in_flight.pop(0).wait()
+            in_flight.append(all_gather_result_blocks(env._result_block, out=gathered[n_gathers[0] % RING], async_op=True)[1])
             n_gathers[0] += 1
             if os.environ.get("FG_BENCH_SYNC_GATHER"):      # (experiment switch: no overlap with the next rollout)
                 finish_gathers()
 
     def finish_gathers():
-        if in_flight[0] is not None:
-            in_flight[0].wait()
-            in_flight[0] = None
+        while in_flight:
+            in_flight.pop(0).wait()
 
     def step_device(s):
         env.launch(s["params"], state=s["state"], keep_state=True)
@@ -517,7 +521,7 @@ def main():
                                 envs_per_gpu=B, n_params=N_PARAMS, sigma=args.sigma, max_episode_steps=200,
                                 contexts="device sampler (numpy-exact PCG64 streams, fg_reset)", parallelism=f"env-shard x{world}",
                                 l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
-                                collective="all_gather(return,length,flags) per step, overlapped with the next rollout" if world > 1 else "none"),
+                                collective="all_gather(return,length,flags) per step, asynchronous behind the next rollouts (ring of %d result sets)" % RING if world > 1 else "none"),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_sync=e2e_sync, e2e_graph=e2e_graph,
                     clocks=clocks, gpu_launches=K)

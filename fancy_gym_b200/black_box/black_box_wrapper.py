@@ -38,7 +38,8 @@ class BlackBoxWrapper(Wrapper):
                  reward_aggregation: Callable[[np.ndarray], float] = np.sum,
                  max_planning_times: int = np.inf,
                  condition_on_desired: bool = False,
-                 wall_mode: int = 0):
+                 wall_mode: int = 0,
+                 result_sets: int = 2):
         super().__init__(env)
         self.duration = duration
         self.learn_sub_trajectories = learn_sub_trajectories
@@ -82,14 +83,16 @@ class BlackBoxWrapper(Wrapper):
         self.traj_gen.device = self.device
         B, n = self.num_envs, base.n_links
         dev = self.device
-        # Two sets of result buffers used alternately: what step() returns stays valid until the step after the next
+        # A ring of result buffer sets (two by default): what step() returns stays valid until the step after the next
         # one, without a device-side copy per call.
         self._obs_index_np = np.asarray(self._obs_index())
         # (return | length | flags) of a step live in ONE contiguous byte block: the multi-GPU exchange is a single
         # all-gather of that block, with no packing kernels (fancy_gym_b200/dist).
         from ..dist import result_block_bytes, result_block_flag_bytes, result_block_views
         self._out_sets = []
-        for _ in range(2):
+        if int(result_sets) < 2:
+            raise ValueError("result_sets must be >= 2 (what step() returns stays valid while the next step runs)")
+        for _ in range(int(result_sets)):      # > 2: consumers on other streams (multi-GPU exchange) may lag several steps
             block = torch.zeros(result_block_bytes(B), dtype=torch.uint8, device=dev)
             r, ln, fl = result_block_views(block, B)
             self._out_sets.append(dict(block=block, ret=r, len=ln, flags=fl, flag_bytes=result_block_flag_bytes(block, B),
@@ -131,7 +134,7 @@ class BlackBoxWrapper(Wrapper):
         share one episode (replanning / sub-trajectories) their last observation and infos are carried over; the "unbounded"
         HoleReacher reward keeps per-episode state in info[:, 2:4] (fg_rollout_io.info)."""
         self._prev_info, self._prev_obs = self._info, self._obs
-        self._out_i ^= 1
+        self._out_i = (self._out_i + 1) % len(self._out_sets)
         self._bind_outputs()
         if getattr(self._base, "rew_fct", None) == "unbounded":
             self._info[:, 2:4] = self._prev_info[:, 2:4]

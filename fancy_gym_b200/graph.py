@@ -87,6 +87,7 @@ class EpisodePipeline:
             raise NotImplementedError("EpisodePipeline runs one plan per episode")
         if not env._fast_reset:
             raise NotImplementedError("EpisodePipeline needs the device-side reset (context_sampler='device')")
+        assert len(env._out_sets) >= self.SLOTS
         self.env = env
         dev = env.device
         B, P = env.num_envs, env.action_space.shape[0]
