@@ -159,11 +159,19 @@ __device__ __forceinline__ bool self_collision(const double (&q)[N], const doubl
                                                const float (&sn)[N]) {
   // any(q > pi) or any(q < -pi): |q| > pi as an unsigned compare of the sign-stripped bit patterns (non-negative doubles
   // order like integers) — two integer compares per joint instead of the double-precision max chain ptxas builds
+  // Fast screen on the HIGH words only: non-negative float patterns order like the integers they are, so the largest
+  // sign-stripped high word is one FMNMX(3) chain with |.| modifiers; only when it reaches pi's high word (|q| within 2^-20
+  // of pi or beyond: rare) are the full 64-bit patterns compared.
   bool lim = false;
   constexpr unsigned long long kPiBits = 0x400921FB54442D18ULL;
+  float hi_max = 0.f;
 #pragma unroll
-  for (int i = 0; i < N; ++i)
-    lim |= ((unsigned long long)__double_as_longlong(q[i]) & 0x7FFFFFFFFFFFFFFFULL) > kPiBits;
+  for (int i = 0; i < N; ++i) hi_max = fmaxf(hi_max, fabsf(__int_as_float(__double2hiint(q[i]))));
+  if (hi_max >= __int_as_float(0x400921FB)) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      lim |= ((unsigned long long)__double_as_longlong(q[i]) & 0x7FFFFFFFFFFFFFFFULL) > kPiBits;
+  }
   if constexpr (N < 3) {
     return lim;
   } else {

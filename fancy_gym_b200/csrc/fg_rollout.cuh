@@ -236,7 +236,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   // ---- MP set-up ----
   float dmp_y[N], dmp_yd[N];        // DMP integrator state (scaled-time velocity)
   float pos_next[N];                // ProMP: pos[t+1] carried to the next step
-  float vel_prev[N];
+  float pos[N], vel[N];             // desired position / velocity of the current step
   const float r_tau = __frcp_rn(c.tau), r_dt = __frcp_rn(c.dt_f);
   if constexpr (MP == FG_MP_DMP) {
 #pragma unroll
@@ -249,14 +249,13 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
     for (int d = 0; d < N; ++d) {
       pos_next[d] = dot_row(tabA, d, K);
-      vel_prev[d] = 0.f;
+      vel[d] = 0.f;                 // (a one-point plan has zero velocity; otherwise overwritten at t = 0)
     }
   }
 
   double ret = 0.0;
   int t = 0;
   bool terminated = false, truncated = false, success = false, collided = false;
-  float pos[N], vel[N];
   double info0 = 0, info1 = 0;
 
   const int my_steps = io.seg_steps_env ? min(seg_steps, io.seg_steps_env[b]) : seg_steps;      // ragged sub-trajectories
@@ -273,12 +272,8 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
           const float acc = dot_row(row, d, K);
           pos_next[d] = acc;
           vel[d] = div_by(__fsub_rn(acc, pos[d]), dtt, rdt);     // (pos[t+1]-pos[t]) / (times[t+1]-times[t])
-          vel_prev[d] = vel[d];
         }
-      } else {
-#pragma unroll
-        for (int d = 0; d < N; ++d) vel[d] = vel_prev[d];
-      }
+      }                     // t == T - 1: vel[T-1] = vel[T-2] — the registers simply keep the previous step's values
     } else if constexpr (MP == FG_MP_DMP) {
 #pragma unroll
       for (int d = 0; d < N; ++d) {
@@ -386,18 +381,18 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
         success = false;
         if (c.rew_fct == 0) {
           // hr_simple_reward.py:35-53
-          double dist_cost = 0.0, coll_cost = 0.0;
+          // ordinary steps: (-0.0 + x) + -0.0 == x for x = acc_cost * -5e-8 <= 0, so only the product is formed
+          reward = __dmul_rn(acc_cost, -5e-8);
           if (steps == 199 || collided) {
             double ex, ey;
             end_effector64<N>(th, ex, ey);
             const double dx = ex - cx0, dy = ey - (-cx2);
             const double dist = sqrt(dx * dx + dy * dy);
-            dist_cost = dist * dist;
-            coll_cost = collided ? 1.0 : 0.0;
+            const double dist_cost = dist * dist;
+            const double coll_cost = collided ? 1.0 : 0.0;
             success = (dist < 0.005) && !collided;
+            reward = __dadd_rn(__dadd_rn(__dmul_rn(dist_cost, -1.0), reward), __dmul_rn(coll_cost, -c.penalty));
           }
-          reward = __dadd_rn(__dadd_rn(__dmul_rn(dist_cost, -1.0), __dmul_rn(acc_cost, -5e-8)),
-                             __dmul_rn(coll_cost, -c.penalty));
         } else if (c.rew_fct == 1) {
           // hr_dist_vel_acc_reward.py:20-60: distance / collision terms only on step 199 (a collision ends the episode, so
           // the latched flag and collision_dist are this step's); factors (-1, -1e-4, -1e-6, -penalty, 0)
