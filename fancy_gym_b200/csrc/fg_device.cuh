@@ -262,29 +262,25 @@ __device__ __forceinline__ bool wall_collision(const float* __restrict__ s_m, co
                                                const float (&sn)[N], const Hole& h, int wall_mode) {
   bool hit = false;
   const float ythr = fmaxf(0.f, h.nd);
-  // joint positions first, then ONE test whether any link reaches below the ground line at all (the common case in the
-  // sigma = 0.25 regime is "none": a single branch instead of N divergent ones)
-  float Xs[N], Ys[N];
-  unsigned below = 0;
-  {
-    float X = 0.f, Y = 0.f;
+  // ONE test whether any link reaches below the ground line at all (the common case in the sigma = 0.25 regime is
+  // "none"): a link's lower end is one of its two joints, so "some link has min(Y_i, Y_i+1) < ythr" is "the lowest joint is
+  // below ythr" — the joint heights and one FMNMX chain; the x positions and the per-link tests are only formed behind it
+  float Ys[N + 1];
+  Ys[0] = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) Ys[i + 1] = fmaf(sn[i], 1.0f, Ys[i]);      // sample m=99 (s=1) == next joint
+  float ymin = 0.f;
+#pragma unroll
+  for (int i = 1; i <= N; ++i) ymin = fminf(ymin, Ys[i]);
+  if (ymin < ythr || wall_mode == 2) {           // mode 2: no skipping at all
+    float X = 0.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      Xs[i] = X;
-      Ys[i] = Y;
-      const float Y1 = fmaf(sn[i], 1.0f, Y);      // sample m=99 (s=1) == next joint
-      below |= (fminf(Y, Y1) < ythr) ? (1u << i) : 0u;
+      if (wall_mode == 2 || fminf(Ys[i], Ys[i + 1]) < ythr)
+        hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], X, Ys[i], h)
+                                : link_wall_brute(s_m, cs[i], sn[i], X, Ys[i], h);
       X = fmaf(cs[i], 1.0f, X);
-      Y = Y1;
     }
-  }
-  if (wall_mode == 2) below = (1u << N) - 1;      // mode 2: no skipping at all
-  if (below) {
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      if (below & (1u << i))
-        hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], Xs[i], Ys[i], h)
-                                : link_wall_brute(s_m, cs[i], sn[i], Xs[i], Ys[i], h);
   }
   return hit;
 }
