@@ -55,7 +55,11 @@ __host__ __device__ constexpr int traj_rec4(int mp, int kw) {
 // in float32.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sincos_reduced(double th, float& s, float& c) {
-  const double kd = rint(th * 0.63661977236758138243);               // 2/pi
+  // k = nearest integer to th * 2/pi by the 1.5 * 2^52 shift: one DFMA + one DADD, and the quadrant is the low word of the
+  // shifted sum (|k| < 2^31) — instead of DMUL + FRND.F64 + F2I.F64 (the two conversions run on the slow conversion path)
+  constexpr double kShift = 6755399441055744.0;
+  const double shifted = fma(th, 0.63661977236758138243, kShift);    // 2/pi
+  const double kd = shifted - kShift;
   double r = fma(-kd, 1.57079632679489655800e+00, th);               // pi/2 hi
   r = fma(-kd, 6.12323399573676603587e-17, r);                       // pi/2 lo
   const float x = (float)r, x2 = x * x;                              // |x| <= pi/4
@@ -66,7 +70,7 @@ __device__ __forceinline__ void sincos_reduced(double th, float& s, float& c) {
   cp = fmaf(cp, x2, 4.166664568298827e-2f);
   cp = fmaf(cp, x2, -0.5f);
   cp = fmaf(cp, x2, 1.0f);
-  const int q = (int)kd;
+  const int q = __double2loint(shifted);
   float ss = (q & 1) ? cp : sp;
   float cc = (q & 1) ? sp : cp;
   s = (q & 2) ? -ss : ss;
