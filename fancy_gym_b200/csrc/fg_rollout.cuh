@@ -108,6 +108,10 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   // velocity IS the last float32 action (or the zeros of reset), so it is carried as float32: no conversions per step and
   // ten registers less; it is float64 only at the HBM boundary.  PD-controlled / torque envs keep the float64 value.
   constexpr bool VF = !MOTOR && (ENV == FG_ENV_HOLE_REACHER || ENV == FG_ENV_VIAPOINT_REACHER);
+  // The register-resident-weights instantiation (KC > 0) is dispatched for velocity / motor control only (position control
+  // takes the run-time-K variant, fg_rollout_launch.cuh): without a motor law the action IS the desired velocity, so the desired
+  // position is dead weight in the loop — no copies of it, no select per joint, for ProDMP no position contraction at all.
+  constexpr bool VEL_ONLY = (KC > 0) && !MOTOR;
   double q[N], v[N];
   float vf[N];
 #pragma unroll
@@ -323,7 +327,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     } else {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        const float des = (c.ctrl == FG_CTRL_VELOCITY) ? vel[i] : pos[i];
+        const float des = (VEL_ONLY || c.ctrl == FG_CTRL_VELOCITY) ? vel[i] : pos[i];
         a32[i] = fminf(fmaxf(des, -c.act_lim), c.act_lim);
         a64[i] = (double)a32[i];
       }
@@ -543,6 +547,12 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     io.done[b] = stopped ? 1 : 0;
   }
   if (io.write_cond && len > 0 && (stopped || io.write_cond == 2)) {
+    if constexpr (VEL_ONLY && (MP == FG_MP_PROMP || MP == FG_MP_PRODMP)) {
+      // the desired position is not carried through the loop in this instantiation: the same FMA chain, once, here
+      const float* row = tabA + (len - 1) * RA;
+#pragma unroll
+      for (int i = 0; i < N; ++i) pos[i] = dot_row(row, i, MP == FG_MP_PROMP ? K : K + 3);
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       io.cond_pos[b * N + i] = pos[i];

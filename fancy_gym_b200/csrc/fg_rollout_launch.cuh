@@ -40,7 +40,9 @@ cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, in
   // num_basis = 5 is the registry default of every MP type (registry.py:76-125): register-resident weights
   // (instantiated for the registered link counts only — 5 links, SimpleReacher's 2 — to keep the library small)
   if constexpr (MP != FG_MP_TRAJ && (N == 5 || N == 2)) {
-    if (c.K == 5) return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why);
+    // (without a motor law the KC instantiation assumes velocity control: position control takes the run-time-K variant)
+    if (c.K == 5 && (MOTOR || c.ctrl == FG_CTRL_VELOCITY))
+      return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why);
   }
   return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why);
 }
