@@ -43,10 +43,10 @@ OPS_PER_ENV_STEP = 4356          # SURVEY.md §8d, HoleReacher/ProMP (FMA = 2, e
 TRAJ_BYTES_PER_ENV = 2 * 200 * 5 * 4 + N_PARAMS * 4   # fg_trajgen: pos + vel out, params in
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at
 # the same sizes (profiles/r1_rollout_ncu_summary.txt, profiles/r1_trajgen_ncu_summary.txt)
-NCU_TRAFFIC_ROLLOUT = 14_299_136 + 0
+NCU_TRAFFIC_ROLLOUT = 14_299_648 + 0
 NCU_TRAFFIC_TRAJGEN = 26_288_384 + 2_039_226_000
-NCU_WARP_INSTRUCTIONS_ROLLOUT = 182_538_154     # smsp__inst_executed.sum of the same capture
-NCU_PIPES_ROLLOUT = dict(issue_active=70.2, alu=42.4, fma=31.8, xu=14.8, fp64=11.1)
+NCU_WARP_INSTRUCTIONS_ROLLOUT = 177_580_561     # smsp__inst_executed.sum of the same capture
+NCU_PIPES_ROLLOUT = dict(issue_active=70.8, alu=41.8, fma=32.3, xu=15.3, fp64=11.5)
 
 
 # ------------------------------------------------------------------------------------------------
