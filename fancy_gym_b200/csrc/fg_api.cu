@@ -242,6 +242,9 @@ fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const f
   for (int k = 0; k < 17; ++k) a.scale[k] = pb->scale[k];
   if ((pb->n_steps_env != nullptr) != (pb->times_table != nullptr))
     return fail(FG_ERR_INVALID, "fg_trajgen_phase: n_steps_env and times_table go together");
+  if (pb->n_steps_env && pb->times_stride < h->cfg.n_steps)
+    return fail(FG_ERR_INVALID, "fg_trajgen_phase: times_stride %d is shorter than the longest plan (%d points)",
+                pb->times_stride, h->cfg.n_steps);
   a.n_steps_env = pb->n_steps_env; a.times_table = pb->times_table; a.times_stride = pb->times_stride;
   int prev = 0;
   FG_CUDA(cudaGetDevice(&prev));
