@@ -9,6 +9,8 @@
 // The fused rollout consumes the result through FG_MP_TRAJ (8 KB per env from HBM: far below its compute time).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fg_device.cuh"
 #include "fg_dispatch.h"
 #include "fg_trajgen.cuh"
@@ -149,6 +151,133 @@ __global__ void __launch_bounds__(256, FG_PHASE_MINB) k_trajgen_phase(const __gr
   for (int i = T * N + threadIdx.x; i < TM * N; i += blockDim.x) gp[i] = gv[i] = 0.f;        // ragged: rows past this env's plan
 }
 
+// The same evaluation with ONE WARP per env (the default; the block-per-env kernel above stays as the fallback behind
+// FG_PHASE_BLOCK=1 and as the reference the two are tested against each other with).  A block per env spends most of its
+// time in its own latency chain — parameters -> barrier -> float64 basis -> barrier -> difference -> barrier -> store — with
+// 4 blocks per SM to overlap; a warp per env needs no block barrier, 32 time points per pass go through a 1.3 KB per-warp
+// stage, and 24-32 independent envs are in flight per SM.  ProMP's forward difference needs the NEXT point: a pass advances
+// by 31 points and lane 31 only supplies that neighbour (it is re-evaluated as lane 0 of the next pass); the last point
+// copies the velocity of the one before it, across a pass boundary through a carried row.
+constexpr int kPhaseWarps = 4;
+constexpr int kPhaseRows = 32;
+constexpr int kPhaseWarpFloats = FG_MAX_DOF * 17 + (2 * kPhaseRows + 1) * FG_MAX_DOF;
+
+template <int MPK, int NT>
+__global__ void __launch_bounds__(kPhaseWarps * 32, (MPK == FG_MP_PRODMP) ? 6 : 8)
+k_trajgen_phase_warp(const __grid_constant__ PhaseArgs a, const long long B) {
+  __shared__ float s_all[kPhaseWarps][kPhaseWarpFloats];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * kPhaseWarps + warp;
+  if (b >= B) return;                          // whole warps leave together; the kernel has no block barrier
+  const int N = a.N, TM = a.T, K = a.K;
+  const int KP = (MPK == FG_MP_PROMP) ? K : K + 1;
+  float* s_w = s_all[warp];                    // [N, KP] this env's parameters
+  float* st_p = s_w + FG_MAX_DOF * 17;         // [32, N] positions of this pass (DMP: the forcing term)
+  float* st_v = st_p + kPhaseRows * FG_MAX_DOF;   // [32, N] velocities of this pass
+  float* st_c = st_v + kPhaseRows * FG_MAX_DOF;   // [N]     velocity row carried across a pass boundary (ProMP)
+  const int T = a.n_steps_env ? min(max(a.n_steps_env[b], 2), TM) : TM;
+  const float* times = a.n_steps_env ? a.times_table + (long long)T * a.times_stride : a.times;
+  const float tau = a.tau[b], delay = a.delay[b];
+  for (int i = lane; i < N * KP; i += 32) {
+    float p = a.params[b * N * KP + i];
+    if (MPK == FG_MP_DMP) p = __fmul_rn(p, (i % KP < K) ? a.wscale : a.gscale);
+    if (MPK == FG_MP_PRODMP && a.rel_goal && (i % KP) == K) p = __fadd_rn(p, a.bc_pos[b * N + i / KP]);
+    s_w[i] = p;
+  }
+  if (lane < N) st_c[lane] = 0.f;
+  __syncwarp();
+
+  // ProDMP: boundary-condition row of the pre-integrated bases (same for every time point of the env)
+  int ib = 0;
+  double y1b = 0, y2b = 0, dy1b = 0, dy2b = 0, det = 1;
+  auto index_of = [&](float t32) {
+    const float z = fmaxf(__fdiv_rn(__fsub_rn(t32, delay), tau), 0.f);
+    const int i = (int)rintf(__fdiv_rn(z, a.scaled_dt));
+    return min(max(i, 0), a.n_pc - 1);
+  };
+  if constexpr (MPK == FG_MP_PRODMP) {
+    ib = index_of(a.init_time);
+    y1b = a.pc_y[ib * 4]; y2b = a.pc_y[ib * 4 + 1]; dy1b = a.pc_y[ib * 4 + 2]; dy2b = a.pc_y[ib * 4 + 3];
+    det = y1b * dy2b - y2b * dy1b;
+  }
+
+  constexpr int STEP = (MPK == FG_MP_PROMP) ? kPhaseRows - 1 : kPhaseRows;
+  float* gp = a.pos + b * TM * N;
+  float* gv = a.vel + b * TM * N;
+  for (int t0 = 0; t0 < T; t0 += STEP) {
+    const int t = t0 + lane;
+    const bool valid = t < T;
+    if (valid) {
+      if constexpr (MPK == FG_MP_PRODMP) {
+        constexpr int KG = NT;        // == K + 1 (checked by the launcher)
+        const int ix = index_of(times[t]);
+        const double y1 = a.pc_y[ix * 4], y2 = a.pc_y[ix * 4 + 1], dy1 = a.pc_y[ix * 4 + 2], dy2 = a.pc_y[ix * 4 + 3];
+        const double xi1 = dy2b / det * y1 - dy1b / det * y2, xi2 = y1b / det * y2 - y2b / det * y1;
+        const double xi3 = dy2b / det * dy1 - dy1b / det * dy2, xi4 = y1b / det * dy2 - y2b / det * dy1;
+        float hp[NT], hv[NT];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+          hp[k] = (float)((a.pc_pos[ix * KG + k] - xi1 * a.pc_pos[ib * KG + k] - xi2 * a.pc_vel[ib * KG + k]) * a.scale[k]);
+          hv[k] = (float)((a.pc_vel[ix * KG + k] - xi3 * a.pc_pos[ib * KG + k] - xi4 * a.pc_vel[ib * KG + k]) * a.scale[k]);
+        }
+        const float x1 = (float)xi1, x2 = (float)xi2, x3 = (float)xi3, x4 = (float)xi4;
+        for (int d = 0; d < N; ++d) {
+          const float yb = a.bc_pos[b * N + d], vb = __fmul_rn(a.bc_vel[b * N + d], tau);
+          float ap = fmaf(x2, vb, fmaf(x1, yb, 0.f)), av = fmaf(x4, vb, fmaf(x3, yb, 0.f));     // table columns 0, 1
+#pragma unroll
+          for (int k = 0; k < NT; ++k) {
+            ap = fmaf(hp[k], s_w[d * KP + k], ap);
+            av = fmaf(hv[k], s_w[d * KP + k], av);
+          }
+          st_p[lane * N + d] = ap;
+          st_v[lane * N + d] = __fdiv_rn(av, tau);
+        }
+      } else if constexpr (NT <= kMaxRbf) {
+        const float un = __fdiv_rn(__fsub_rn(times[t], delay), tau);       // float32 elementwise ops of the library
+        const float z = fminf(fmaxf(un, 0.f), 1.f);
+        double phi[NT];
+        const double x = eval_basis<NT>(a, z, phi);
+        float coef[NT];
+#pragma unroll
+        for (int kk = 0; kk < NT; ++kk)
+          coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk]);
+        for (int d = 0; d < N; ++d) {
+          float acc = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < NT; ++kk)          // FMA chain in index order over the weighted functions
+            if (kk >= a.first && kk < a.first + K) acc = fmaf(coef[kk], s_w[d * KP + kk - a.first], acc);
+          st_p[lane * N + d] = acc;
+        }
+      }
+    }
+    __syncwarp();
+    if constexpr (MPK == FG_MP_PROMP) {
+      if (t < T - 1 && lane < STEP) {
+        const float dtt = __fsub_rn(times[t + 1], times[t]);
+        for (int d = 0; d < N; ++d)
+          st_v[lane * N + d] = __fdiv_rn(__fsub_rn(st_p[(lane + 1) * N + d], st_p[lane * N + d]), dtt);
+      }
+      __syncwarp();
+      if (t == T - 1 && lane < STEP)                 // vel[T-1] = vel[T-2] (0 for a one-point plan: the carried row starts at 0)
+        for (int d = 0; d < N; ++d) st_v[lane * N + d] = (lane > 0) ? st_v[(lane - 1) * N + d] : st_c[d];
+      if (lane == STEP - 1 && t < T - 1)
+        for (int d = 0; d < N; ++d) st_c[d] = st_v[lane * N + d];
+      __syncwarp();
+    }
+    const int rows = min(STEP, T - t0);
+    for (int i = lane; i < rows * N; i += 32) {
+      if constexpr (MPK == FG_MP_DMP) {
+        gv[t0 * N + i] = st_p[i];      // the forcing term goes to the velocity buffer (k_dmp_integrate_phase works in place)
+      } else {
+        gp[t0 * N + i] = st_p[i];
+        gv[t0 * N + i] = st_v[i];
+      }
+    }
+    __syncwarp();
+  }
+  for (int i = T * N + lane; i < TM * N; i += 32) gp[i] = gv[i] = 0.f;          // ragged: rows past this env's plan
+}
+
 // DMP with a per-env phase, second half: semi-implicit Euler in scaled time, every op rounded separately (the library's
 // recurrence).  A lane owns one (env, dof) pair and a warp G = 32 / N envs, like k_trajgen_dmp; the forcing term comes from
 // the velocity buffer (written by k_trajgen_phase) and is replaced in place, CH time points at a time through a per-warp
@@ -252,7 +381,11 @@ static cudaError_t launch_dmp_integrate(const PhaseArgs& a, long long B, cudaStr
 }
 
 template <int MPK, int NT>
-static cudaError_t launch_phase_nt(const PhaseArgs& a, long long B, cudaStream_t stream, size_t smem) {
+static cudaError_t launch_phase_nt(const PhaseArgs& a, long long B, cudaStream_t stream, size_t smem, bool block_per_env) {
+  if (!block_per_env) {
+    k_trajgen_phase_warp<MPK, NT><<<(unsigned)((B + kPhaseWarps - 1) / kPhaseWarps), kPhaseWarps * 32, 0, stream>>>(a, B);
+    return cudaGetLastError();
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_trajgen_phase<MPK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -264,13 +397,14 @@ static cudaError_t launch_phase_nt(const PhaseArgs& a, long long B, cudaStream_t
 }
 
 template <int MPK>
-static cudaError_t launch_phase_mp(const PhaseArgs& a, long long B, cudaStream_t stream, size_t smem, const char** why) {
+static cudaError_t launch_phase_mp(const PhaseArgs& a, long long B, cudaStream_t stream, size_t smem, bool block_per_env,
+                                   const char** why) {
   const int nt = (MPK == FG_MP_PRODMP) ? a.K + 1 : a.n_total;
-#define FG_NT(n) case n: return launch_phase_nt<MPK, n>(a, B, stream, smem);
+#define FG_NT(n) case n: return launch_phase_nt<MPK, n>(a, B, stream, smem, block_per_env);
   switch (nt) {
     FG_NT(1) FG_NT(2) FG_NT(3) FG_NT(4) FG_NT(5) FG_NT(6) FG_NT(7) FG_NT(8) FG_NT(9) FG_NT(10) FG_NT(11) FG_NT(12)
     FG_NT(13) FG_NT(14) FG_NT(15) FG_NT(16)
-    case 17: if constexpr (MPK == FG_MP_PRODMP) return launch_phase_nt<MPK, 17>(a, B, stream, smem);
+    case 17: if constexpr (MPK == FG_MP_PRODMP) return launch_phase_nt<MPK, 17>(a, B, stream, smem, block_per_env);
   }
 #undef FG_NT
   *why = "at most 16 basis functions";
@@ -280,15 +414,18 @@ static cudaError_t launch_phase_mp(const PhaseArgs& a, long long B, cudaStream_t
 cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t stream, int max_smem_optin, const char** why) {
   const int KP = (a.mp_kind == FG_MP_PROMP) ? a.K : a.K + 1;
   const size_t smem = sizeof(float) * ((size_t)2 * a.T * a.N + (size_t)a.N * KP);
-  if (smem > (size_t)max_smem_optin) {
-    *why = "trajectory too long for the per-env-phase kernel";
+  // one warp per env by default; FG_PHASE_BLOCK=1 selects the block-per-env kernel (kept for A/B tests; it also needs the
+  // whole trajectory in shared memory, which the warp kernel does not)
+  static const bool block_per_env = [] { const char* e = getenv("FG_PHASE_BLOCK"); return e && atoi(e) > 0; }();
+  if (block_per_env && smem > (size_t)max_smem_optin) {
+    *why = "trajectory too long for the block-per-env phase kernel";
     return cudaSuccess;
   }
   cudaError_t e = cudaSuccess;
   switch (a.mp_kind) {
-    case FG_MP_PROMP: e = launch_phase_mp<FG_MP_PROMP>(a, B, stream, smem, why); break;
-    case FG_MP_DMP: e = launch_phase_mp<FG_MP_DMP>(a, B, stream, smem, why); break;
-    case FG_MP_PRODMP: e = launch_phase_mp<FG_MP_PRODMP>(a, B, stream, smem, why); break;
+    case FG_MP_PROMP: e = launch_phase_mp<FG_MP_PROMP>(a, B, stream, smem, block_per_env, why); break;
+    case FG_MP_DMP: e = launch_phase_mp<FG_MP_DMP>(a, B, stream, smem, block_per_env, why); break;
+    case FG_MP_PRODMP: e = launch_phase_mp<FG_MP_PRODMP>(a, B, stream, smem, block_per_env, why); break;
     default: *why = "unknown mp_kind"; return cudaSuccess;
   }
   if (*why) return cudaSuccess;
