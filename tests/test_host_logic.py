@@ -223,3 +223,52 @@ def test_replanning_schedule_is_evaluated_on_the_host():
     assert env._segment_steps(env.traj_gen.n_steps) == (10, True)
     env.plan_steps = 3                                     # planning budget exhausted: run to the end
     assert env._segment_steps(env.traj_gen.n_steps) == (env.traj_gen.n_steps, False)
+
+
+# ---- ragged sub-trajectories and the ring of result sets: host side (no kernel runs) ------------------------------
+def test_ragged_plan_lengths_and_time_grids_follow_the_oracle():
+    """learn_sub_trajectories with a different learned tau per env: env b plans round(tau_b / dt) points (clamped to 2 .. the
+    longest admissible plan), buffers are sized for the longest plan, and row n of the per-length time-grid table is the
+    float32 grid the oracle (and the library: torch.linspace) builds for an n-point plan — bit for bit."""
+    import torch
+    from oracle.mp import time_grid
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=6, device="cpu",
+                         mp_config_override={"black_box_kwargs": {"learn_sub_trajectories": True}})
+    tg = env.traj_gen
+    P = env.action_space.shape[0]
+    params = torch.zeros(6, P)
+    params[:, 0] = torch.tensor([0.37, 0.8, 0.02, 2.0, 0.015, 1.234])
+    tg.reset()
+    tg.set_params(params)
+    tg.set_duration(None, 0.01)
+    t_max = int(round(float(tg.phase_gn.tau_bound[1]) / 0.01))
+    assert tg.n_steps == t_max and tg.n_steps_env.dtype == torch.int32
+    want = np.clip(np.round(params[:, 0].double().numpy() / 0.01), 2, t_max).astype(np.int32)
+    assert np.array_equal(tg.n_steps_env.numpy(), want) and len(set(want.tolist())) > 3
+    tab = tg._times_table().numpy()
+    assert tab.shape == (t_max + 1, t_max) and tab.dtype == np.float32
+    for n in (2, 37, 80, 123, t_max):
+        ref = time_grid(float(n * 0.01), 0.01, 0.0, "mirror")
+        assert np.array_equal(tab[n, :n], ref.astype(np.float32)) and not tab[n, n:].any()
+    # equal learned taus collapse to the shared-table path: no per-env lengths
+    params[:, 0] = 0.5
+    tg.reset()
+    tg.set_params(params)
+    tg.set_duration(None, 0.01)
+    assert tg.n_steps_env is None and tg.n_steps == 50
+
+
+def test_result_set_ring():
+    """what step() returns lives in a ring of result sets (two by default; more for consumers that lag several steps)"""
+    with pytest.raises(ValueError):
+        fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=2, device="cpu",
+                       mp_config_override={"black_box_kwargs": {"result_sets": 1}})
+    for n in (2, 4):
+        env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=2, device="cpu",
+                             mp_config_override={"black_box_kwargs": {"result_sets": n}})
+        seen = []
+        for _ in range(2 * n):
+            env._flip_outputs()
+            seen.append(env._ret.data_ptr())
+            assert env._result_block.data_ptr() == env._out_sets[env._out_i]["block"].data_ptr()
+        assert len(set(seen)) == n and seen[:n] == seen[n:]
