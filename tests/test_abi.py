@@ -107,3 +107,14 @@ def test_hot_kernels_keep_their_register_budget():
     assert all(v <= 128 for n, v in regs.items() if "k_rollout" in n), "a rollout instantiation exceeds 128 registers"
     cov = [n for n in regs if "k_cov_simtILi5" in n]
     assert cov and all(regs[n] <= 64 for n in cov)
+
+
+def test_integration_stub_lists_the_abi_structs_field_for_field():
+    """the ctypes stub printed in INTEGRATION.md (what a fancy_gym maintainer would paste) has to stay the ABI"""
+    import re
+    from fancy_gym_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class FgConfig\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n\nclass", doc, re.S)
+    assert re.findall(r'\("(\w+)"', m.group(1)) == [f[0] for f in _lib.FgConfig._fields_]
+    m = re.search(r"class FgRolloutIO\(C\.Structure\):.*?\n\ndef check", doc, re.S)
+    assert re.findall(r'"(\w+)"', m.group(0)) == [f[0] for f in _lib.FgRolloutIO._fields_]
