@@ -360,8 +360,11 @@ class BlackBoxWrapper(Wrapper):
                 dbg["obs"] = torch.zeros(B, T, self.env.observation_space.shape[0], dtype=torch.float32, device=self.device)
         planned = self._planned_trajectory(local) if self.verbose >= 2 else None   # before the state moves on
         self.launch(local, seg, replan_break, dbg, keep_state=_keep_state)
-        if self.condition_on_desired and not _keep_state:
-            self.condition_set = True      # every live env breaks at the same step or is done
+        if self.condition_on_desired and replan_break and not _keep_state:
+            # the desired state is recorded on a BREAK only (black_box_wrapper.py:196-201): at a re-planning break every
+            # live env breaks at the same step (the kernel wrote its row); a plan that simply runs out records nothing, and
+            # rows written by terminated / truncated envs belong to finished episodes
+            self.condition_set = True
 
         if not _keep_state:
             self.current_traj_steps += seg     # live envs all advance by `seg`; finished envs are frozen

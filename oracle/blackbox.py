@@ -136,8 +136,13 @@ class BlackBoxOracle:
         clipped = np.clip(action, self.bounds[0], self.bounds[1])
         self.traj_gen.set_params(clipped)
         init_time = np.array(0 if not self.do_replanning else self.current_traj_steps * self.dt)
-        cpos = self.condition_pos if self.condition_pos is not None else self.env.current_pos
-        cvel = self.condition_vel if self.condition_vel is not None else self.env.current_vel
+        # per env: the recorded desired state once THAT env's loop has broken, its current state before (each env of the
+        # batch is its own wrapper in the reference: :110-111)
+        cpos, cvel = self.env.current_pos, self.env.current_vel
+        if self.condition_pos is not None:
+            m = self.condition_has[:, None]
+            cpos = np.where(m, self.condition_pos.astype(np.float64), cpos)      # (float32 -> float64 is exact)
+            cvel = np.where(m, self.condition_vel.astype(np.float64), cvel)
         self.traj_gen.set_initial_conditions(init_time, cpos, cvel)
         self.traj_gen.set_duration(duration, self.dt)
         return self.traj_gen.get_traj_pos(), self.traj_gen.get_traj_vel()
@@ -199,15 +204,17 @@ class BlackBoxOracle:
                                                    t + 1 + self.current_traj_steps)) \
                 and self.plan_steps < self.max_planning_times
             stop = run & (term | trunc | replan)
-            n_valid = getattr(self.traj_gen, "n_valid", None)
-            if n_valid is not None:          # ragged sub-trajectories: an env's plan ends after its own number of steps
-                stop = stop | (run & (t + 1 >= n_valid))
-            if self.condition_on_desired and stop.any():
+            if self.condition_on_desired and stop.any():      # only a BREAK records the desired state (:196-201)
                 if new_cond_pos is None:
-                    new_cond_pos = np.array(env.current_pos, dtype=pos.dtype)
-                    new_cond_vel = np.array(env.current_vel, dtype=vel.dtype)
+                    new_cond_pos = np.zeros_like(pos)
+                    new_cond_vel = np.zeros_like(vel)
+                    self.condition_has = np.zeros(B, bool)
                 new_cond_pos[stop] = pos[stop]
                 new_cond_vel[stop] = vel[stop]
+                self.condition_has = self.condition_has | stop
+            n_valid = getattr(self.traj_gen, "n_valid", None)
+            if n_valid is not None:          # ragged sub-trajectories: an env's plan simply ends after its own number of
+                stop = stop | (run & (t + 1 >= n_valid))      # steps (the reference's for loop runs out: no break)
             brk = brk | stop
             self.done = self.done | (run & (term | trunc))
         if self.condition_on_desired:

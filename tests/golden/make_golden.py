@@ -175,9 +175,13 @@ def n_params_of(env_id):
     return cfg["env"]["n_links"] * per_dof
 
 
-def params_for(env_id, seed, n_plans):
+def params_for(env_id, seed, n_plans, sub_traj=False):
     rng = np.random.default_rng(1234 + seed)
-    return (0.5 * rng.standard_normal((n_plans, n_params_of(env_id)))).astype(np.float32)
+    th = (0.5 * rng.standard_normal((n_plans, n_params_of(env_id)))).astype(np.float32)
+    if sub_traj:      # learn_sub_trajectories: the learned tau leads the parameter vector; a different one per env and plan
+        tau = rng.choice(np.array([0.17, 0.25, 0.37, 0.5, 0.8], dtype=np.float32), size=(n_plans, 1))
+        th = np.concatenate([tau, th], axis=1)
+    return th
 
 
 _REPLAN25 = dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4)
@@ -205,6 +209,13 @@ BB_CASES = [
     ("bb_holereacher_promp_unbounded", "fancy_ProMP/HoleReacher-v0", list(range(8)), {}, dict(rew_fct="unbounded")),
     ("bb_holereacher_prodmp_unbounded_replan", "fancy_ProDMP/HoleReacher-v0", list(range(6)),
      dict(replanning_schedule=lambda p, v, o, a, t: t % 60 == 0, condition_on_desired=True), dict(rew_fct="unbounded")),
+    # sequencing (learn_sub_trajectories): every plan is round(tau / dt) points long, tau differs per env and plan, so the
+    # batched paths see RAGGED plans; condition_on_desired only takes effect on a break (black_box_wrapper.py:196-201)
+    ("bb_simplereacher_prodmp_subtraj", "fancy_ProDMP/SimpleReacher-v0", list(range(6)), dict(learn_sub_trajectories=True)),
+    ("bb_simplereacher_prodmp_subtraj_cod", "fancy_ProDMP/SimpleReacher-v0", list(range(6)),
+     dict(learn_sub_trajectories=True, condition_on_desired=True)),
+    ("bb_viapoint_dmp_subtraj", "fancy_DMP/ViaPointReacher-v0", list(range(6)), dict(learn_sub_trajectories=True)),
+    ("bb_holereacher_promp_subtraj", "fancy_ProMP/HoleReacher-v0", list(range(6)), dict(learn_sub_trajectories=True)),
 ]
 
 
@@ -213,29 +224,39 @@ def bb_case(case):
     return (*case, {}) if len(case) == 4 else case
 
 
-def gen_bb(ns):
+T_PAD = 200      # rows the planned trajectories of sub-trajectory cases are zero-padded to (max_episode_steps)
+
+
+def gen_bb(ns, only=None):
     for fname, env_id, seeds, bbk, env_over in map(bb_case, BB_CASES):
-        n_plans = 8 if bbk.get("replanning_schedule") else 1
+        if only and only not in fname:
+            continue
+        sub_traj = bool(bbk.get("learn_sub_trajectories"))
+        n_plans = 8 if (bbk.get("replanning_schedule") or sub_traj) else 1
         rec = {k: [] for k in ("obs0", "params", "positions", "velocities", "step_obs", "step_rewards",
-                               "ret", "length", "terminated", "truncated", "obs", "n_calls")}
+                               "ret", "length", "terminated", "truncated", "obs", "n_calls", "n_points")}
         for s in seeds:
             bb = build_reference_bb(ns, env_id, "shipped", bbk, env_over)
             ob0, _ = bb.reset(seed=s)
-            th = params_for(env_id, s, n_plans)
+            th = params_for(env_id, s, n_plans, sub_traj)
             per = {k: [] for k in rec if k not in ("obs0", "params", "n_calls")}
             calls = 0
             for i in range(n_plans):
                 ob, ret, te, tr, info = bb.step(th[i])
                 calls += 1
                 L = info["trajectory_length"]
-                T = info["positions"].shape[0]
+                n_pts = info["positions"].shape[0]
+                T = T_PAD if sub_traj else n_pts
+                pos_pad = np.zeros((T, info["positions"].shape[1]), np.float32)
+                vel_pad = np.zeros_like(pos_pad)
+                pos_pad[:n_pts], vel_pad[:n_pts] = info["positions"], info["velocities"]
                 so = np.zeros((T, info["step_observations"].shape[1]), np.float32)
                 so[:L] = info["step_observations"]
                 sr = np.zeros(T)
                 sr[:L] = info["step_rewards"]
-                for k, v in (("positions", info["positions"]), ("velocities", info["velocities"]), ("step_obs", so),
+                for k, v in (("positions", pos_pad), ("velocities", vel_pad), ("step_obs", so),
                              ("step_rewards", sr), ("ret", ret), ("length", L), ("terminated", te),
-                             ("truncated", tr), ("obs", ob)):
+                             ("truncated", tr), ("obs", ob), ("n_points", n_pts)):
                     per[k].append(np.asarray(v))
                 if te or tr:
                     break
@@ -262,8 +283,9 @@ def gen_bb(ns):
                     continue
                 L = out["length"][b, i]
                 assert info["trajectory_length"][b] == L, (fname, b, i, info["trajectory_length"][b], L)
-                assert np.array_equal(info["positions"][b], out["positions"][b, i]), (fname, b, i)
-                assert np.array_equal(info["velocities"][b], out["velocities"][b, i]), (fname, b, i)
+                n = out["n_points"][b, i]
+                assert np.array_equal(info["positions"][b][:n], out["positions"][b, i][:n]), (fname, b, i)
+                assert np.array_equal(info["velocities"][b][:n], out["velocities"][b, i][:n]), (fname, b, i)
                 assert np.array_equal(info["step_observations"][b, :L], out["step_obs"][b, i, :L]), (fname, b, i)
                 assert close64(info["step_rewards"][b, :L], out["step_rewards"][b, i, :L]), (fname, b, i)
                 assert close64(ret[b], out["ret"][b, i]), (fname, b, i, ret[b], out["ret"][b, i])
@@ -276,6 +298,8 @@ def gen_bb(ns):
 if __name__ == "__main__":
     assert rl.available(), "needs /root/reference"
     ns = rl.load()
-    gen_env_kat(ns)
-    gen_bb(ns)
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None      # e.g. --only subtraj
+    if only is None:
+        gen_env_kat(ns)
+    gen_bb(ns, only)
     print("golden vectors written to", HERE)
