@@ -315,6 +315,14 @@ class BlackBoxWrapper(Wrapper):
         io.keep_state = int(bool(keep_state))
         io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
         io.use_cond = int(self.condition_set)
+        if not per_env_phase:
+            # an assumption switch may move the state the plan starts from (mp/assumptions.py: DMP recurrence from t0)
+            src = (self._cond_pos, self._cond_vel) if self.condition_set else (st.q.to(torch.float32), st.v.to(torch.float32))
+            pre = self.traj_gen.boundary_prestep(params, *src)
+            if pre is not None:
+                self._cond_pos.copy_(pre[0])
+                self._cond_vel.copy_(pre[1])
+                io.use_cond = 1
         io.write_cond = (2 if replan_break else 1) if self.condition_on_desired else 0
         io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
         io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()

@@ -36,7 +36,8 @@ cudaError_t launch_traj_cov(const CovArgs& a, long long B, int path, cudaStream_
 struct PhaseArgs {
   int mp_kind, N, T, K;             // K weighted basis functions per dof
   int phase_kind, n_total, first;   // phase 0 linear / 1 exp; RBF count incl. zero padding; first weighted RBF
-  double alpha_phase;
+  int exp_right_clip;               // exponential phase of the clipped (1) or only left-bounded (0) linear phase
+  double alpha_phase, basis_scale;  // basis_scale: DMP forcing-basis factor (1 unless weights_scale sits on the basis)
   double cen[16], bw[16];
   float wscale, gscale, alpha, beta;
   const float* times;               // [T] float32 time grid (device)

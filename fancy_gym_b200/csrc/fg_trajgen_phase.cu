@@ -110,14 +110,14 @@ __global__ void __launch_bounds__(256, FG_PHASE_MINB) k_trajgen_phase(const __gr
   } else if constexpr (NT <= kMaxRbf) {
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
       const float un = __fdiv_rn(__fsub_rn(times[t], delay), tau);       // float32 elementwise ops of the library
-      const float z = fminf(fmaxf(un, 0.f), 1.f);
+      const float z = fminf(fmaxf(un, 0.f), (a.phase_kind && !a.exp_right_clip) ? INFINITY : 1.f);
       double phi[NT];
       const double x = eval_basis<NT>(a, z, phi);
       // coefficient of weighted basis function k = kk - first (float32, rounded once like the host-built tables)
       float coef[NT];
 #pragma unroll
       for (int kk = 0; kk < NT; ++kk)
-        coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk]);
+        coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk] * a.basis_scale);
       for (int d = 0; d < N; ++d) {
         float acc = 0.f;
 #pragma unroll
@@ -234,13 +234,13 @@ k_trajgen_phase_warp(const __grid_constant__ PhaseArgs a, const long long B) {
         }
       } else if constexpr (NT <= kMaxRbf) {
         const float un = __fdiv_rn(__fsub_rn(times[t], delay), tau);       // float32 elementwise ops of the library
-        const float z = fminf(fmaxf(un, 0.f), 1.f);
+        const float z = fminf(fmaxf(un, 0.f), (a.phase_kind && !a.exp_right_clip) ? INFINITY : 1.f);
         double phi[NT];
         const double x = eval_basis<NT>(a, z, phi);
         float coef[NT];
 #pragma unroll
         for (int kk = 0; kk < NT; ++kk)
-          coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk]);
+          coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk] * a.basis_scale);
         for (int d = 0; d < N; ++d) {
           float acc = 0.f;
 #pragma unroll

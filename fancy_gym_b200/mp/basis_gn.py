@@ -44,7 +44,7 @@ class NormalizedRBFBasisGenerator:
         tau, delay = pg._tau0, pg._delay0
         dist = tau / (K - 2 * self.num_basis_outside - 1)
         centres_t = np.linspace(-self.num_basis_outside * dist + delay, tau + self.num_basis_outside * dist + delay, K)
-        cp = pg.unbound_phase64_of_time(centres_t)
+        cp = pg.centre_phase64_of_time(centres_t)
         spacing = np.concatenate([cp[1:] - cp[:-1], cp[-1:] - cp[-2:-1]])
         return cp, float(self.basis_bandwidth_factor) / spacing ** 2
 
@@ -57,7 +57,7 @@ class NormalizedRBFBasisGenerator:
         return b
 
     def learnable_basis32(self, times32: np.ndarray) -> np.ndarray:
-        lin = self.phase_generator.linear_phase32(times32)
+        lin = self.phase_generator.phase_argument32(times32)
         b = self.basis64(lin).astype(np.float32)
         z0 = self.first_learnable
         return np.ascontiguousarray(b[..., z0:z0 + self.num_basis])
@@ -116,7 +116,8 @@ class ProDMPBasisGenerator(NormalizedRBFBasisGenerator):
         dy2 = -0.5 * a * y2 + y1
         q1 = (0.5 * a * z - 1) * np.exp(0.5 * a * z) + 1
         q2 = 0.5 * a * (np.exp(0.5 * a * z) - 1)
-        lin = np.clip(z, 0, 1)                        # grid times map back to linear phase z (clipped for x)
+        # grid times map back to linear phase z (clipped for x unless switch exp_phase_right_clip is off)
+        lin = np.clip(z, 0, 1 if pg.assume["exp_phase_right_clip"] else None)
         x = pg.phase64(lin)
         b = self.basis64(lin)
         e = np.exp(a * z / 2)
@@ -145,3 +146,19 @@ class ProDMPBasisGenerator(NormalizedRBFBasisGenerator):
             raise RuntimeError("Time is beyond the pre-computation range.")
         sd32 = f32(f32(self.dt) / f32(pg._tau0))
         return np.rint((z / sd32).astype(f32)).astype(np.int64)
+
+    def lookup(self, table: np.ndarray, times) -> np.ndarray:
+        """rows of a pre-computed table at the given times: nearest grid index (the default) or, switch prodmp_interpolate,
+        linear interpolation in the index z / scaled_dt"""
+        pg = self.phase_generator
+        if not pg.assume["prodmp_interpolate"]:
+            return table[self.indices(times)]
+        f32 = np.float32      # the scaled time is a float32 tensor in the library; the interpolation weight is formed from it
+        z = np.maximum((np.asarray(times, dtype=np.float64) - f32(pg.scalar_delay())) / f32(pg.scalar_tau()), 0.0)
+        z = z.astype(f32).astype(np.float64)
+        if z.size and z.max() > self.pre_compute_length_factor:
+            raise RuntimeError("Time is beyond the pre-computation range.")
+        idx = z / self.scaled_dt
+        i0 = np.clip(np.floor(idx).astype(np.int64), 0, table.shape[0] - 2)
+        fr = (idx - i0)[..., None] if table.ndim > 1 else (idx - i0)
+        return table[i0] * (1 - fr) + table[i0 + 1] * fr

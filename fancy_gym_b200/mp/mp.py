@@ -93,7 +93,16 @@ class MPInterface:
         params = torch.as_tensor(params)
         if params.shape[-1] != self.num_params:
             raise ValueError(f"expected {self.num_params} params, got {tuple(params.shape)}")
-        self.params = self.phase_gn.set_params(params)
+        self.params = self._prepare_local(self.phase_gn.set_params(params))
+
+    def _prepare_local(self, local):
+        """hook: the MP parameters as the kernels consume them (identity unless an assumption switch moves a scale / offset
+        onto the parameters, mp/assumptions.py)"""
+        return local
+
+    def boundary_prestep(self, params, pos, vel):
+        """hook: boundary condition the kernels should start from instead of (pos, vel); None = as given"""
+        return None
 
     def set_initial_conditions(self, init_time, init_pos, init_vel):
         self.init_time = float(np.asarray(init_time if not torch.is_tensor(init_time) else init_time.cpu()))
@@ -160,12 +169,16 @@ class MPInterface:
             if self._pc_dev is None:
                 self._pc_dev = tuple(torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.device)
                                      for x in (bg.pc_pos_basis, bg.pc_vel_basis, bg.pc_y))
+            if pg.assume["prodmp_interpolate"]:
+                raise NotImplementedError("prodmp_interpolate: only the shared-table path (no per-env tau / delay)")
             pb.pc_pos, pb.pc_vel, pb.pc_y = (x.data_ptr() for x in self._pc_dev)
             pb.n_pc = int(bg.pc_y.shape[0])
             pb.scaled_dt = float(np.float32(np.float32(bg.dt) / np.float32(pg._tau0)))
             pb.init_time = float(np.float32(self.init_time))
             for k, v in enumerate(self.weights_goal_scale()):
                 pb.scale[k] = float(v)
+        pb.exp_right_clip = int(bool(pg.assume["exp_phase_right_clip"]))
+        pb.basis_scale = float(self._forcing_basis_scale()) if self.mp_kind == _lib.MP_DMP else 1.0
         if self.n_steps_env is not None:
             tt = self._times_table()
             pb.n_steps_env, pb.times_table, pb.times_stride = self.n_steps_env.data_ptr(), tt.data_ptr(), tt.shape[1]
@@ -212,6 +225,10 @@ class MPInterface:
             return x.expand(B, N).contiguous() if x.dim() < 2 else x.contiguous()
 
         bp, bv = bc(self.init_pos), bc(self.init_vel)
+        if bp is not None and bv is not None:
+            pre = self.boundary_prestep(p, bp, bv)
+            if pre is not None:
+                bp, bv = pre
         if out is None:
             pos = torch.empty(B, T, N, device=self.device, dtype=torch.float32)
             vel = torch.empty_like(pos)
@@ -243,7 +260,9 @@ class MPInterface:
             raise NotImplementedError(f"{type(self).__name__} is not a probabilistic MP")
         self.params_L = None if params_L is None else torch.as_tensor(params_L)
 
-    def _run_traj_cov(self, want_cov, want_std, reg=1e-4, batch_scope=False, path=0):
+    def _run_traj_cov(self, want_cov, want_std, reg=1e-4, batch_scope=None, path=0):
+        if batch_scope is None:
+            batch_scope = self.phase_gn.assume["cov_reg_batch_global"]
         if getattr(self, "params_L", None) is None:
             raise RuntimeError("set_mp_params_variances() must be called first")
         L = self.params_L.to(self.device, torch.float32)
@@ -267,11 +286,11 @@ class MPInterface:
             cov, std = (cov[0] if want_cov else None), (std[0] if want_std else None)
         return cov, std
 
-    def get_traj_pos_cov(self, reg: float = 1e-4, batch_scope: bool = False, path: int = 0):
+    def get_traj_pos_cov(self, reg: float = 1e-4, batch_scope: bool = None, path: int = 0):
         """[.., dof*T, dof*T] float32, dof-major rows / columns (d * T + t)"""
         return self._run_traj_cov(True, False, reg, batch_scope, path)[0]
 
-    def get_traj_pos_std(self, reg: float = 1e-4, batch_scope: bool = False):
+    def get_traj_pos_std(self, reg: float = 1e-4, batch_scope: bool = None):
         """[.., T, dof]: sqrt of the regularised covariance diagonal (the full matrix is never materialised)"""
         return self._run_traj_cov(False, True, reg, batch_scope)[1]
 
@@ -299,25 +318,82 @@ class ProMP(MPInterface):
     def _num_local_params(self):
         return self.num_dof * self.basis_gn.num_basis
 
+    def _basis_scale(self) -> float:
+        return float(self.weights_scale) if self.phase_gn.assume["scale_on_library_side"] else 1.0
+
+    def _prepare_local(self, local):
+        if not self.phase_gn.assume["scale_on_library_side"]:       # the scale sits on the parameters (one float32 multiply)
+            local = local.to(torch.float32) * float(np.float32(self.weights_scale))
+        return local
+
     def tables(self) -> MPTables:
         t32 = self.times32()
         b = self.basis_gn.learnable_basis32(t32)
-        tab_a = (b * np.float32(self.weights_scale)).astype(np.float32)
+        tab_a = (b * np.float32(self._basis_scale())).astype(np.float32)
         tab_b = np.diff(t32).astype(np.float32)
         # (weights_scale is folded into tab_a; the per-env-phase kernel, which has no table, takes it from the config)
         return MPTables(mp_kind=self.mp_kind, n_basis=self.basis_gn.num_basis, n_steps=len(t32), tab_a=tab_a, tab_b=tab_b,
-                        tau=self.phase_gn.scalar_tau(), weights_scale=float(self.weights_scale))
+                        tau=self.phase_gn.scalar_tau(), weights_scale=self._basis_scale())
 
 
 class DMP(MPInterface):
     """Semi-implicit Euler of  y'' = alpha (beta (g - y) - y') + x Phi w  in scaled time (App. B.6)."""
     mp_kind = _lib.MP_DMP
 
-    def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, alpha=25, **kwargs):
+    def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, alpha=25, goal_offset=0.0, **kwargs):
         super().__init__(basis_gn, num_dof, weights_scale, **kwargs)
         self.goal_scale = goal_scale
+        self.goal_offset = float(goal_offset)
         self.alpha = alpha
         self.beta = alpha / 4
+
+    def _forcing_basis_scale(self) -> float:
+        """DMP: the library scales the parameters; with the switch flipped the scale sits on the forcing basis"""
+        return 1.0 if self.phase_gn.assume["scale_on_library_side"] else float(self.weights_scale)
+
+    def _param_weights_scale(self) -> float:
+        return float(self.weights_scale) if self.phase_gn.assume["scale_on_library_side"] else 1.0
+
+    def _prepare_local(self, local):
+        if self.goal_offset:       # goal = goal_scale * theta_g + offset (switch goal_offset_after_scale) in parameter units
+            off = self.goal_offset / float(self.goal_scale) if self.phase_gn.assume["goal_offset_after_scale"] else self.goal_offset
+            local = local.to(torch.float32).clone()
+            local.view(*local.shape[:-1], self.num_dof, -1)[..., -1] += float(np.float32(off))
+        return local
+
+    def boundary_prestep(self, params, pos, vel):
+        """switch dmp_init_on_first_grid_point = False: the Euler recurrence starts at the boundary time t0 itself, so the
+        state the kernels start from (the plan's first grid point) is one step further.  A handful of elementwise float32
+        ops on [B, dof] (the kernels' own recurrence, float32; the forcing contraction is a plain sum here)."""
+        pg = self.phase_gn
+        if pg.assume["dmp_init_on_first_grid_point"]:
+            return None
+        dev, f32 = self.device, torch.float32
+        p = params.to(dev, f32).reshape(-1, self.num_dof, self.basis_gn.num_basis + 1)
+        B = p.shape[0]
+        tau, delay = pg.per_env(B, dev)
+        t0 = torch.tensor(float(np.float32(self.init_time)), dtype=f32, device=dev)
+        t1 = torch.tensor(float(self.times32()[0]), dtype=f32, device=dev)
+        z0, z1 = torch.clamp((t0 - delay) / tau, min=0), torch.clamp((t1 - delay) / tau, min=0)
+        h = (z1 - z0)[:, None]
+        arg = z0 if not pg.assume["exp_phase_right_clip"] else torch.clamp(z0, max=1)
+        x = torch.exp(-pg.alpha_phase * arg.double())
+        cen = torch.as_tensor(self.basis_gn.centers_p, device=dev)
+        bw = torch.as_tensor(self.basis_gn.bandwidth, device=dev)
+        phi = torch.exp(-((x[:, None] - cen) ** 2 * bw) / 2)
+        if self.basis_gn.total_num_basis > 1:
+            phi = phi / phi.sum(-1, keepdim=True)
+        z = self.basis_gn.first_learnable
+        xb = (x[:, None] * phi * self._forcing_basis_scale()).to(f32)[:, z:z + self.basis_gn.num_basis]
+        w = p[..., :-1] * float(np.float32(self._param_weights_scale()))
+        g = p[..., -1] * float(np.float32(self.goal_scale))
+        f = (xb[:, None, :] * w).sum(-1)
+        y = pos.to(dev, f32).expand(B, self.num_dof)
+        yd = vel.to(dev, f32).expand(B, self.num_dof) * tau[:, None]
+        a = float(self.alpha) * (float(self.beta) * (g - y) - yd) + f
+        yd1 = yd + h * a
+        y1 = y + h * yd1
+        return y1.contiguous(), (yd1 / tau[:, None]).contiguous()
 
     @property
     def _num_local_params(self):
@@ -326,12 +402,14 @@ class DMP(MPInterface):
     def tables(self) -> MPTables:
         pg = self.phase_gn
         t32 = self.times32()
-        lin = pg.linear_phase32(t32)
-        xb = (pg.phase64(lin)[:, None] * self.basis_gn.basis64(lin)).astype(np.float32)
+        lin = pg.phase_argument32(t32)
+        z = self.basis_gn.first_learnable
+        xb = (pg.phase64(lin)[:, None] * self.basis_gn.basis64(lin) * self._forcing_basis_scale()).astype(np.float32)
+        xb = np.ascontiguousarray(xb[:, z:z + self.basis_gn.num_basis])
         sc = pg.linear_phase32(t32, clip_hi=False)            # left-bounded scaled time, float32 ops
         tab_b = np.diff(sc).astype(np.float32)
         return MPTables(mp_kind=self.mp_kind, n_basis=self.basis_gn.num_basis, n_steps=len(t32), tab_a=xb, tab_b=tab_b,
-                        tau=pg.scalar_tau(), dmp_alpha=float(self.alpha), weights_scale=float(self.weights_scale),
+                        tau=pg.scalar_tau(), dmp_alpha=float(self.alpha), weights_scale=self._param_weights_scale(),
                         goal_scale=float(self.goal_scale))
 
 
@@ -342,12 +420,13 @@ class ProDMP(MPInterface):
     probabilistic = True
 
     def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, auto_scale_basis=False,
-                 relative_goal=False, disable_weights=False, disable_goal=False, **kwargs):
+                 relative_goal=False, disable_weights=False, disable_goal=False, goal_offset=0.0, **kwargs):
         assert isinstance(basis_gn, ProDMPBasisGenerator)      # trajectory_generator_factory.py:16-17
         if disable_weights or disable_goal:
             raise NotImplementedError("disable_weights / disable_goal are not used by any fancy_gym config")
         super().__init__(basis_gn, num_dof, weights_scale, **kwargs)
         self.goal_scale = goal_scale
+        self.goal_offset = float(goal_offset)
         self.auto_scale_basis = auto_scale_basis
         self.relative_goal = relative_goal
 
@@ -360,26 +439,48 @@ class ProDMP(MPInterface):
         s = np.zeros(K + 1)
         s[:K] = self.weights_scale
         s[K] = self.goal_scale
+        if not self.phase_gn.assume["scale_on_library_side"]:      # the scales sit on the parameters (_prepare_local)
+            s[:] = 1.0
         if self.auto_scale_basis:
             s = s * self.basis_gn.auto_basis_scale_factors
         return s
 
+    def _prepare_local(self, local):
+        A = self.phase_gn.assume
+        on_basis = A["scale_on_library_side"]
+        if on_basis and not self.goal_offset:
+            return local
+        K = self.basis_gn.num_basis
+        local = local.to(torch.float32).clone()
+        v = local.view(*local.shape[:-1], self.num_dof, K + 1)
+        gs = float(self.goal_scale)
+        if not on_basis:
+            sc = torch.full((K + 1,), float(np.float32(self.weights_scale)), dtype=torch.float32, device=local.device)
+            sc[K] = float(np.float32(gs))
+            v *= sc
+        if self.goal_offset:
+            if A["goal_offset_after_scale"]:
+                off = self.goal_offset / gs if on_basis else self.goal_offset
+            else:
+                off = self.goal_offset if on_basis else self.goal_offset * gs
+            v[..., -1] += float(np.float32(off))
+        return local
+
     def tables(self) -> MPTables:
         bg = self.basis_gn
         t32 = self.times32()
-        idx = bg.indices(t32.astype(np.float64))
-        ib = bg.indices(np.float64(np.float32(self.init_time)))
-        y1, y2, dy1, dy2 = (bg.pc_y[idx, j] for j in range(4))
-        y1b, y2b, dy1b, dy2b = (bg.pc_y[ib, j] for j in range(4))
-        pb, vb = bg.pc_pos_basis[ib], bg.pc_vel_basis[ib]
+        t64, tb64 = t32.astype(np.float64), np.float64(np.float32(self.init_time))
+        y1, y2, dy1, dy2 = (bg.lookup(bg.pc_y, t64)[..., j] for j in range(4))
+        y1b, y2b, dy1b, dy2b = (bg.lookup(bg.pc_y, tb64)[..., j] for j in range(4))
+        pb, vb = bg.lookup(bg.pc_pos_basis, tb64), bg.lookup(bg.pc_vel_basis, tb64)
         det = y1b * dy2b - y2b * dy1b
         xi1 = dy2b / det * y1 - dy1b / det * y2
         xi2 = y1b / det * y2 - y2b / det * y1
         xi3 = dy2b / det * dy1 - dy1b / det * dy2
         xi4 = y1b / det * dy2 - y2b / det * dy1
         s = self.weights_goal_scale()
-        pos_h = (bg.pc_pos_basis[idx] - xi1[:, None] * pb - xi2[:, None] * vb) * s
-        vel_h = (bg.pc_vel_basis[idx] - xi3[:, None] * pb - xi4[:, None] * vb) * s
+        pos_h = (bg.lookup(bg.pc_pos_basis, t64) - xi1[:, None] * pb - xi2[:, None] * vb) * s
+        vel_h = (bg.lookup(bg.pc_vel_basis, t64) - xi3[:, None] * pb - xi4[:, None] * vb) * s
         tab_a = np.concatenate([xi1[:, None], xi2[:, None], pos_h], axis=1).astype(np.float32)
         tab_b = np.concatenate([xi3[:, None], xi4[:, None], vel_h], axis=1).astype(np.float32)
         return MPTables(mp_kind=self.mp_kind, n_basis=bg.num_basis, n_steps=len(t32), tab_a=tab_a, tab_b=tab_b,

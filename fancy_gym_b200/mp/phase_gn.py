@@ -12,12 +12,15 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .assumptions import ASSUMPTIONS
+
 
 class PhaseGenerator:
     kind = "linear"
 
     def __init__(self, tau: float = 3.0, delay: float = 0.0, learn_tau: bool = False, learn_delay: bool = False,
                  tau_bound=None, delay_bound=None, **kwargs):
+        self.assume = dict(ASSUMPTIONS)      # the readings of mp_pytorch this generator is built under (mp/assumptions.py)
         self._tau0 = float(tau)
         self._delay0 = float(delay)
         self.learn_tau = bool(learn_tau)
@@ -106,6 +109,10 @@ class PhaseGenerator:
         z = (times32.astype(np.float32) - delay) / tau
         return np.clip(z, 0, 1 if clip_hi else None).astype(np.float32)
 
+    def phase_argument32(self, times32: np.ndarray) -> np.ndarray:
+        """the scaled time the canonical phase is a function of: the linear phase clipped to [0, 1]"""
+        return self.linear_phase32(times32)
+
     def phase64(self, lin) -> np.ndarray:
         """canonical phase in float64 from a linear phase"""
         return np.asarray(lin, dtype=np.float64)
@@ -113,6 +120,13 @@ class PhaseGenerator:
     def unbound_phase64_of_time(self, t64):
         """canonical phase (unbounded) of absolute times with the construction-time tau / delay"""
         return (np.asarray(t64, dtype=np.float64) - self._delay0) / self._tau0
+
+    def centre_phase64_of_time(self, t64):
+        """where an RBF centre placed at time t sits in phase space (switch centres_through_unbounded_phase)"""
+        if self.assume["centres_through_unbounded_phase"]:
+            return self.unbound_phase64_of_time(t64)
+        z = np.clip((np.asarray(t64, dtype=np.float64) - self._delay0) / self._tau0, 0, 1)
+        return self.phase64(z)
 
 
 class LinearPhaseGenerator(PhaseGenerator):
@@ -122,12 +136,16 @@ class LinearPhaseGenerator(PhaseGenerator):
 class ExpDecayPhaseGenerator(PhaseGenerator):
     kind = "exp"
 
-    def __init__(self, tau: float = 3.0, delay: float = 0.0, alpha_phase: float = 3.0, learn_tau: bool = False,
+    def __init__(self, tau: float = 3.0, delay: float = 0.0, alpha_phase: float = None, learn_tau: bool = False,
                  learn_delay: bool = False, learn_alpha_phase: bool = False, **kwargs):
         if learn_alpha_phase:
             raise NotImplementedError("learn_alpha_phase is not used by any fancy_gym config")
-        self.alpha_phase = float(alpha_phase)
         super().__init__(tau, delay, learn_tau, learn_delay, **kwargs)
+        self.alpha_phase = float(self.assume["alpha_phase_default"] if alpha_phase is None else alpha_phase)
+
+    def phase_argument32(self, times32: np.ndarray) -> np.ndarray:
+        """switch exp_phase_right_clip: x = exp(-alpha z) of the clipped linear phase, or of the left-bounded one"""
+        return self.linear_phase32(times32, clip_hi=bool(self.assume["exp_phase_right_clip"]))
 
     def phase64(self, lin) -> np.ndarray:
         return np.exp(-self.alpha_phase * np.asarray(lin, dtype=np.float64))

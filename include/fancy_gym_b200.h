@@ -254,6 +254,9 @@ typedef struct fg_phase_basis {
   const int32_t* n_steps_env;
   const float* times_table;
   int32_t times_stride;
+  /* readings of mp_pytorch that are kept switchable (fancy_gym_b200/mp/assumptions.py; the defaults are 1 and 1.0) */
+  int32_t exp_right_clip;      /* exponential phase: 1 = x = exp(-alpha * clip(z, 0, 1)), 0 = exp(-alpha * max(z, 0)) */
+  double basis_scale;          /* DMP: factor on the forcing basis x * Phi (weights_scale when it is not on the parameters) */
 } fg_phase_basis;
 
 /*

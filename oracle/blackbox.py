@@ -254,7 +254,7 @@ def make_oracle(env_id, mode="mirror", mp_overrides=None, **bb_kwargs):
     tau defaults to the duration, learn_sub_trajectories implies learn_tau, default bounds."""
     cfg = copy.deepcopy(RESOLVED[env_id])
     for k, v in (mp_overrides or {}).items():
-        cfg[k].update(v)
+        cfg[k] = _merge(cfg[k], v)        # (a section that names a `*_type` replaces the base, registry.py:272-274)
     env = BatchedReacher(**cfg["env"])
     duration = 200 * env.dt
     phase = dict(cfg["phase"])

@@ -30,6 +30,59 @@ import numpy as np
 
 F32, F64 = np.float32, np.float64
 
+# ----------------------------------------------------------------------------------------------
+# Named switches for every point where this restatement of mp_pytorch could not be checked against the package
+# (SURVEY.md App. B.8 i-vi plus two more).  The DEFAULT of each switch is what the restatement assumes; flipping one
+# gives the alternative reading.  fancy_gym_b200/mp/assumptions.py holds the same table for the CUDA path (a CPU test keeps
+# the two in step) and DESIGN.md carries the sensitivity of every BASELINE env to every switch
+# (tools/mp_sensitivity.py).  A generator captures the switches when it is constructed.
+# ----------------------------------------------------------------------------------------------
+ASSUMPTIONS = {
+    # B.8 (i)  DMP: the first grid point t0 + dt carries the initial state (set_duration(include_init_time=False) drops t0 and
+    #          the Euler recurrence starts on the first remaining point).  False: the recurrence starts at t0 itself and the
+    #          row of t0 is dropped afterwards (every output row is one Euler step further).
+    "dmp_init_on_first_grid_point": True,
+    # B.8 (ii) weights_scale / goal_scale multiply the BASIS (ProMP, ProDMP) resp. the PARAMETERS (DMP).  False: the other
+    #          way round.  Algebraically identical; float32 rounding differs.
+    "scale_on_library_side": True,
+    # B.8 (iii) default alpha_phase of the exponential phase when a config does not give one (registry.py:112-115, ProDMP)
+    "alpha_phase_default": 3.0,
+    # B.8 (iv) RBF centres are mapped through the UNBOUNDED phase.  False: through the bounded one (identical for
+    #          num_basis_outside = 0, which is every fancy_gym config).
+    "centres_through_unbounded_phase": True,
+    # B.8 (v)  covariance regulariser: max(diag) per sample.  True: over the whole batch (torch.max of a batched tensor).
+    "cov_reg_batch_global": False,
+    # B.8 (vi) goal_offset (kwarg, default 0; no classic_control config sets it) is added AFTER goal_scale.  False: before.
+    "goal_offset_after_scale": True,
+    # exponential phase x = exp(-alpha_phase * z): z is the linear phase clipped to [0, 1].  False: only left-bounded
+    # (z = max((t - delay) / tau, 0)), so x keeps decaying after t = delay + tau.  Matters whenever tau < duration
+    # (fancy_ProDMP/*: tau = 1.5 < 2.0).
+    "exp_phase_right_clip": True,
+    # ProDMP: pre-integrated bases are read at the NEAREST grid index.  True: linear interpolation between grid points.
+    "prodmp_interpolate": False,
+}
+_DEFAULT_ASSUMPTIONS = dict(ASSUMPTIONS)
+
+
+class assume:
+    """context manager: `with assume(exp_phase_right_clip=False): orc = make_oracle(...)`"""
+
+    def __init__(self, **switches):
+        unknown = set(switches) - set(ASSUMPTIONS)
+        if unknown:
+            raise KeyError(f"unknown assumption switch(es): {sorted(unknown)}")
+        self.switches = switches
+
+    def __enter__(self):
+        self.saved = dict(ASSUMPTIONS)
+        ASSUMPTIONS.update(self.switches)
+        return self
+
+    def __exit__(self, *exc):
+        ASSUMPTIONS.clear()
+        ASSUMPTIONS.update(self.saved)
+        return False
+
 
 # ----------------------------------------------------------------------------------------------
 # exact float32 FMA emulation (round-to-odd in float64, then one rounding to float32)
@@ -88,7 +141,7 @@ class PhaseGenerator:
     until reset() ("finalize")."""
 
     def __init__(self, phase_generator_type="linear", tau=3.0, delay=0.0, learn_tau=False,
-                 learn_delay=False, alpha_phase=3.0, learn_alpha_phase=False, tau_bound=None,
+                 learn_delay=False, alpha_phase=None, learn_alpha_phase=False, tau_bound=None,
                  delay_bound=None, alpha_phase_bound=None, mode="gold", **kwargs):
         t = phase_generator_type.lower()
         if t in ("rhythmic", "smooth"):
@@ -98,6 +151,9 @@ class PhaseGenerator:
         self.kind = t
         self.mode = mode
         self.dtype = _dt_of(mode)
+        self.assume = dict(ASSUMPTIONS)
+        if alpha_phase is None:
+            alpha_phase = self.assume["alpha_phase_default"]
         self.tau0, self.delay0, self.alpha0 = float(tau), float(delay), float(alpha_phase)
         self.learn_tau, self.learn_delay = bool(learn_tau), bool(learn_delay)
         self.learn_alpha_phase = bool(learn_alpha_phase) and t == "exp"
@@ -160,7 +216,22 @@ class PhaseGenerator:
     def linear_phase_to_time(self, z):
         return z * self._bc(self.tau) + self._bc(self.delay)
 
+    def exp_argument(self, times):
+        """the scaled time z the exponential phase decays over (switch exp_phase_right_clip)"""
+        return self.linear_phase(times) if self.assume["exp_phase_right_clip"] else self.left_bound_linear_phase(times)
+
     def phase(self, times):
+        if self.kind == "linear":
+            return self.linear_phase(times)
+        return np.exp(-self._bc(self.alpha_phase) * self.exp_argument(times)).astype(self.dtype)
+
+    def phase_argument(self, times):
+        """what the canonical phase is a function of: the clipped linear phase, or (exp phase without the right clip) the
+        left-bounded one"""
+        return self.linear_phase(times) if self.kind == "linear" else self.exp_argument(times)
+
+    def bound_phase(self, times):
+        """canonical phase of the linear phase clipped to [0, 1] (switch centres_through_unbounded_phase = False)"""
         if self.kind == "linear":
             return self.linear_phase(times)
         return np.exp(-self._bc(self.alpha_phase) * self.linear_phase(times)).astype(self.dtype)
@@ -199,7 +270,8 @@ class NormalizedRBFBasis:
             basis_dist = tau / dt(K - 2 * self.num_basis_outside - 1)
             centres_t = np.linspace(-self.num_basis_outside * basis_dist + delay,
                                     tau + self.num_basis_outside * basis_dist + delay, K, dtype=dt)
-            self.centres_p = np.asarray(pg.unbound_phase(centres_t), dtype=dt)
+            through = pg.unbound_phase if pg.assume["centres_through_unbounded_phase"] else pg.bound_phase
+            self.centres_p = np.asarray(through(centres_t), dtype=dt)
             spacing = np.concatenate([self.centres_p[1:] - self.centres_p[:-1],
                                       self.centres_p[-1:] - self.centres_p[-2:-1]])
             self.bandwidth = (dt(self.basis_bandwidth_factor) / spacing ** 2).astype(dt)
@@ -255,13 +327,13 @@ class ProDMPBasis(NormalizedRBFBasis):
     index (interpolate=True switches to linear interpolation, B.8)."""
 
     def __init__(self, phase_generator, num_basis=10, basis_bandwidth_factor=3, num_basis_outside=0,
-                 dt=0.01, alpha=25, pre_compute_length_factor=6, interpolate=False, mode=None, **kwargs):
+                 dt=0.01, alpha=25, pre_compute_length_factor=6, interpolate=None, mode=None, **kwargs):
         assert phase_generator.kind == "exp"      # basis_generator_factory.py:16
         super().__init__(phase_generator, num_basis, basis_bandwidth_factor, num_basis_outside, mode)
         self.alpha = alpha
         self.dt = dt
         self.pre_compute_length_factor = pre_compute_length_factor
-        self.interpolate = interpolate
+        self.interpolate = phase_generator.assume["prodmp_interpolate"] if interpolate is None else interpolate
         self.pre_compute()
 
     @property
@@ -287,7 +359,7 @@ class ProDMPBasis(NormalizedRBFBasis):
         # RBF basis and canonical phase on the grid, with construction-time tau/delay
         delay = float(pg.delay0)
         pc_times = z * tau + delay
-        lin = np.clip((pc_times - delay) / tau, 0, 1)
+        lin = np.clip((pc_times - delay) / tau, 0, 1 if pg.assume["exp_phase_right_clip"] else None)
         x = np.exp(-float(pg.alpha0) * lin)
         cen, bw = _gold_centres(self)
         b = np.exp(-((x[:, None] - cen) ** 2 * bw) / 2)
@@ -419,18 +491,23 @@ class ProMP(MPBase):
     def _num_local_params(self):
         return self.num_dof * self.basis_gn.num_basis
 
+    def _basis_scale(self):
+        return self.weights_scale if self.phase_gn.assume["scale_on_library_side"] else 1.0
+
     def _weights(self):
         w = self.params.reshape(*self.params.shape[:-1], self.num_dof, self.basis_gn.num_basis)
+        if not self.phase_gn.assume["scale_on_library_side"]:
+            w = (w * self.dtype(self.weights_scale)).astype(self.dtype)
         return w
 
     def _scaled_basis_learnable(self):
         """[...,T,K_learnable] = basis * weights_scale restricted to the learnable columns."""
         bg = self.basis_gn
         if self.mode == "mirror":
-            b = _basis_from_linear_phase(bg, self.phase_gn.linear_phase(self.times)).astype(F32)
-            b = (b * F32(self.weights_scale)).astype(F32)
+            b = _basis_from_linear_phase(bg, self.phase_gn.phase_argument(self.times)).astype(F32)
+            b = (b * F32(self._basis_scale())).astype(F32)
         else:
-            b = (bg.basis(self.times) * self.dtype(self.weights_scale)).astype(self.dtype)
+            b = (bg.basis(self.times) * self.dtype(self._basis_scale())).astype(self.dtype)
         z0 = getattr(bg, "num_basis_zero_start", 0)
         return b[..., z0:z0 + bg.num_basis]
 
@@ -482,6 +559,8 @@ def _gold_centres(bg):
     dist = tau / (K - 2 * bg.num_basis_outside - 1)
     ct = np.linspace(-bg.num_basis_outside * dist + delay, tau + bg.num_basis_outside * dist + delay, K)
     cp = (ct - delay) / tau
+    if not pg.assume["centres_through_unbounded_phase"]:
+        cp = np.clip(cp, 0, 1)
     if pg.kind == "exp":
         cp = np.exp(-float(pg.alpha0) * cp)
     sp = np.concatenate([cp[1:] - cp[:-1], cp[-1:] - cp[-2:-1]])
@@ -491,9 +570,10 @@ def _gold_centres(bg):
 class DMP(MPBase):
     """App. B.6.  params per dof: K weights then the goal."""
 
-    def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, alpha=25, mode=None, **kwargs):
+    def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, alpha=25, goal_offset=0.0, mode=None, **kwargs):
         super().__init__(basis_gn, num_dof, weights_scale, mode)
         self.goal_scale = goal_scale
+        self.goal_offset = goal_offset
         self.alpha = alpha
         self.beta = alpha / 4
 
@@ -503,28 +583,42 @@ class DMP(MPBase):
 
     def _split(self):
         dt = self.dtype
+        A = self.phase_gn.assume
         p = self.params.reshape(*self.params.shape[:-1], self.num_dof, self.basis_gn.num_basis + 1)
-        w = (p[..., :-1] * dt(self.weights_scale)).astype(dt)
-        g = (p[..., -1] * dt(self.goal_scale)).astype(dt)
+        w = p[..., :-1]
+        if A["scale_on_library_side"]:          # DMP: the library scales the parameters
+            w = (w * dt(self.weights_scale)).astype(dt)
+        g = _scaled_goal(p[..., -1], self.goal_scale, self.goal_offset, A, dt)
         return w, g
 
-    def _forcing(self, w):
+    def _grid(self):
+        """the time points the recurrence runs over: the plan's grid, or (switch dmp_init_on_first_grid_point = False) the
+        grid with the boundary time t0 in front"""
+        if self.phase_gn.assume["dmp_init_on_first_grid_point"]:
+            return self.times
+        t0 = np.asarray(self.init_time, dtype=F64).astype(self.times.dtype)
+        t0 = np.broadcast_to(t0[..., None] if t0.ndim else t0, (*self.times.shape[:-1], 1))
+        return np.concatenate([t0, self.times], axis=-1)
+
+    def _forcing(self, w, times):
+        scale = 1.0 if self.phase_gn.assume["scale_on_library_side"] else self.weights_scale
         if self.mode == "mirror":
-            lin = self.phase_gn.linear_phase(self.times)
+            lin = self.phase_gn.phase_argument(times)
             xb = (_phase_from_linear_phase(self.phase_gn, lin)[..., None]
-                  * _basis_from_linear_phase(self.basis_gn, lin)).astype(F32)
+                  * _basis_from_linear_phase(self.basis_gn, lin) * scale).astype(F32)
             return fma_chain32(xb, w)
-        x = self.phase_gn.phase(self.times)
-        b = self.basis_gn.basis(self.times)
+        x = self.phase_gn.phase(times)
+        b = (self.basis_gn.basis(times) * self.dtype(scale)).astype(self.dtype)
         return np.einsum("...i,...ik,...jk->...ij", x, b, w).astype(self.dtype)
 
     def _integrate(self):
         dt = self.dtype
         w, g = self._split()
-        f = self._forcing(w)
-        sc = self.phase_gn.left_bound_linear_phase(self.times)
+        times = self._grid()
+        f = self._forcing(w, times)
+        sc = self.phase_gn.left_bound_linear_phase(times)
         sdt = np.diff(sc, axis=-1).astype(dt)
-        T = self.times.shape[-1]
+        T = times.shape[-1]
         batch = np.broadcast_shapes(f.shape[:-2], np.shape(self.init_pos)[:-1])
         pos = np.zeros((*batch, T, self.num_dof), dtype=dt)
         vel = np.zeros_like(pos)
@@ -540,6 +634,8 @@ class DMP(MPBase):
             vel[..., i + 1, :] = vel[..., i, :] + h * acc
             pos[..., i + 1, :] = pos[..., i, :] + h * vel[..., i + 1, :]
         vel = vel / (tau_b[..., None] if np.ndim(tau_b) else tau_b)
+        if T != self.times.shape[-1]:       # the row of t0 is not part of the plan
+            pos, vel = pos[..., 1:, :], vel[..., 1:, :]
         return pos.astype(dt), vel.astype(dt)
 
     def get_traj_pos(self):
@@ -549,14 +645,23 @@ class DMP(MPBase):
         return self._integrate()[1]
 
 
+def _scaled_goal(theta_g, goal_scale, goal_offset, A, dt):
+    """goal parameter -> goal (switch goal_offset_after_scale; the offset is 0 in every classic_control config)"""
+    if A["goal_offset_after_scale"]:
+        g = (theta_g * dt(goal_scale)).astype(dt)
+        return (g + dt(goal_offset)).astype(dt) if goal_offset else g
+    return ((theta_g + dt(goal_offset)) * dt(goal_scale)).astype(dt)
+
+
 class ProDMP(MPBase):
     """App. B.7.  params per dof: K weights then the goal."""
 
     def __init__(self, basis_gn, num_dof, weights_scale=1.0, goal_scale=1.0, auto_scale_basis=False,
-                 relative_goal=False, disable_weights=False, disable_goal=False, mode=None, **kwargs):
+                 relative_goal=False, disable_weights=False, disable_goal=False, goal_offset=0.0, mode=None, **kwargs):
         assert isinstance(basis_gn, ProDMPBasis)   # trajectory_generator_factory.py:16-17
         super().__init__(basis_gn, num_dof, weights_scale, mode)
         self.goal_scale = goal_scale
+        self.goal_offset = goal_offset
         self.auto_scale_basis = auto_scale_basis
         self.relative_goal = relative_goal
         self.disable_weights = disable_weights
@@ -577,6 +682,8 @@ class ProDMP(MPBase):
         s = np.zeros(K + 1)
         s[:K] = self.weights_scale
         s[K] = self.goal_scale
+        if not self.phase_gn.assume["scale_on_library_side"]:     # the scales sit on the parameters instead (_full_params)
+            s[:] = 1.0
         if self.auto_scale_basis:
             s = s * self.basis_gn.auto_basis_scale_factors
         return s
@@ -591,6 +698,20 @@ class ProDMP(MPBase):
             p = np.concatenate([np.zeros((*lead, self.num_dof, K)), p], axis=-1)
         elif self.disable_goal:
             p = np.concatenate([p, np.zeros((*lead, self.num_dof, 1))], axis=-1)
+        A = self.phase_gn.assume
+        if not A["scale_on_library_side"]:
+            sc = np.full(K + 1, float(self.weights_scale))
+            sc[K] = float(self.goal_scale)
+            p = (p.astype(F32) * sc.astype(F32)).astype(F32).astype(F64) if self.mode != "gold" else p * sc
+        if self.goal_offset:
+            p = p.copy()
+            off, gs = float(self.goal_offset), float(self.goal_scale)
+            on_basis = A["scale_on_library_side"]         # the goal column of the basis still multiplies by goal_scale
+            if A["goal_offset_after_scale"]:
+                off = off / gs if on_basis else off       # goal = goal_scale * theta_g + offset
+            else:
+                off = off if on_basis else off * gs       # goal = goal_scale * (theta_g + offset)
+            p[..., -1] = p[..., -1] + off
         if self.relative_goal:
             p = p.copy()
             p[..., -1] = p[..., -1] + np.asarray(self.init_pos, dtype=F64)
@@ -695,12 +816,14 @@ def get_trajectory_generator(trajectory_generator_type, action_dim, basis_genera
 
 # ----------------------------------------------------------------------------------------------
 # trajectory covariance (App. B.5) — PARITY UNPINNED: mp_pytorch is absent and fancy_gym never calls it
-def traj_pos_cov(basis, params_L, num_dof, reg=1e-4, batch_scope=False):
+def traj_pos_cov(basis, params_L, num_dof, reg=1e-4, batch_scope=None):
     """Sigma_y = Psi (L L^T) Psi^T + reg * max(diag Sigma_y) * I in float64.
     basis [T, Kc] (already scaled: weights_scale * Phi for ProMP, the bracketed H = [H_w | H_g] for ProDMP),
     params_L [B, D, D] with D = num_dof * Kc (lower triangle used), rows / columns dof-major (d * T + t).
     Returns (cov [B, dof*T, dof*T], std [B, T, dof]); the max is per env unless batch_scope (mp_pytorch takes torch.max
     over whatever batch it is given; the reference never batches)."""
+    if batch_scope is None:
+        batch_scope = ASSUMPTIONS["cov_reg_batch_global"]
     basis = np.asarray(basis, dtype=F64)
     L = np.tril(np.asarray(params_L, dtype=F64))
     T, Kc = basis.shape

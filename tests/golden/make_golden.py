@@ -13,8 +13,8 @@ What it does
                      restatement (mp_pytorch itself is absent: see oracle/mp.py header), for the
                      three BASELINE envs incl. replanning / condition_on_desired.
   3. asserts that oracle/reacher.py and oracle/blackbox.py reproduce every stored array
-     (bit-exact for obs/flags/lengths, <= 4e-16 relative for float64 rewards: numpy's 1-D
-     `linalg.norm` and the batched sqrt(dx^2+dy^2) may differ by one ulp).
+     (bit-exact for obs/flags/lengths, <= 8e-16 relative for float64 rewards: numpy's 1-D
+     `linalg.norm` and the batched sqrt(dx^2+dy^2) may differ by one ulp, i.e. up to three in the square).
 """
 import importlib
 import os
@@ -60,7 +60,8 @@ def close64(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     same_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
     with np.errstate(invalid="ignore"):
-        ok = same_inf | (np.abs(a - b) <= 4e-16 * np.maximum(np.abs(a), np.abs(b)))
+        # one ulp in a distance becomes up to three ulps (6.7e-16 relative) in its square, the reward's distance term
+        ok = same_inf | (np.abs(a - b) <= 8e-16 * np.maximum(np.abs(a), np.abs(b)))
     return bool(np.all(ok))
 
 
@@ -152,10 +153,35 @@ class TorchTrajGen:
         self.tg.reset()
 
 
-def build_reference_bb(ns, env_id, mode, bb_kwargs, env_over=None):
+def resolved_cfg(env_id, mp_over=None):
+    """the id's resolved config with section overrides ({"ctrl": ..., "basis": ..., "phase": ..., "traj": ...}) applied the
+    way make_oracle applies them"""
+    import copy
+    from oracle.blackbox import _merge
+    cfg = copy.deepcopy(RESOLVED[env_id])
+    for k, v in (mp_over or {}).items():
+        cfg[k] = _merge(cfg[k], v)
+    return cfg
+
+
+_SECTION = {"ctrl": "controller_kwargs", "basis": "basis_generator_kwargs", "phase": "phase_generator_kwargs",
+            "traj": "trajectory_generator_kwargs"}
+
+
+def mp_config_override_of(env_id, mp_over, bb_kwargs=None):
+    """the same overrides as a fancy_gym `mp_config_override` (whole sections, so that the `_type` replace quirk of
+    nested_update, registry.py:272-274, does not drop keys)"""
+    cfg = resolved_cfg(env_id, mp_over)
+    out = {_SECTION[k]: dict(cfg[k]) for k in (mp_over or {})}
+    if bb_kwargs is not None:
+        out["black_box_kwargs"] = dict(bb_kwargs)
+    return out
+
+
+def build_reference_bb(ns, env_id, mode, bb_kwargs, env_over=None, mp_over=None):
     """reference BlackBoxWrapper(MPWrapper([TimeAwareObservation](TimeLimit(env)))) as make_bb
     (utils/make_env_helpers.py:68-136) would assemble it, with the oracle MP as traj_gen."""
-    cfg = RESOLVED[env_id]
+    cfg = resolved_cfg(env_id, mp_over)
     name = env_id.split("/")[1]
     env = ns.TimeLimit(rl.make_step_env(ns, name, **(env_over or {})), 200)
     if bb_kwargs.get("replanning_schedule") or bb_kwargs.get("learn_sub_trajectories"):
@@ -164,26 +190,35 @@ def build_reference_bb(ns, env_id, mode, bb_kwargs, env_over=None):
     wrap = {"HoleReacher-v0": ns.MPWrapper_HoleReacher, "ViaPointReacher-v0": ns.MPWrapper_ViaPoint,
             "SimpleReacher-v0": ns.MPWrapper_SimpleReacher, "LongSimpleReacher-v0": ns.MPWrapper_SimpleReacher}[name]
     env = wrap(env)
-    orc = make_oracle(env_id, mode=mode, mp_overrides={"env": env_over or {}}, **bb_kwargs)   # only for an identically configured traj_gen
+    orc = make_oracle(env_id, mode=mode, mp_overrides=dict(mp_over or {}, env=env_over or {}), **bb_kwargs)   # only for an identically configured traj_gen
     ctrl = ns.get_controller(**cfg["ctrl"])
     return ns.BlackBoxWrapper(env, TorchTrajGen(orc.traj_gen), ctrl, duration=2.0, verbose=2, **bb_kwargs)
 
 
-def n_params_of(env_id):
-    cfg = RESOLVED[env_id]
+def n_params_of(env_id, mp_over=None):
+    cfg = resolved_cfg(env_id, mp_over)
     per_dof = cfg["basis"]["num_basis"] + (0 if cfg["traj"]["trajectory_generator_type"] == "promp" else 1)
     return cfg["env"]["n_links"] * per_dof
 
 
-def params_for(env_id, seed, n_plans, sub_traj=False):
+def params_for(env_id, seed, n_plans, sub_traj=False, mp_over=None):
     rng = np.random.default_rng(1234 + seed)
-    th = (0.5 * rng.standard_normal((n_plans, n_params_of(env_id)))).astype(np.float32)
+    th = (0.5 * rng.standard_normal((n_plans, n_params_of(env_id, mp_over)))).astype(np.float32)
     if sub_traj:      # learn_sub_trajectories: the learned tau leads the parameter vector; a different one per env and plan
         tau = rng.choice(np.array([0.17, 0.25, 0.37, 0.5, 0.8], dtype=np.float32), size=(n_plans, 1))
         th = np.concatenate([tau, th], axis=1)
+    else:             # learned tau / delay lead the parameter vector (tau first): a different phase per env
+        ph = (mp_over or {}).get("phase", {})
+        lead = []
+        if ph.get("learn_tau"):
+            lead.append(rng.uniform(0.9, 2.0, size=(n_plans, 1)).astype(np.float32))
+        if ph.get("learn_delay"):
+            lead.append(rng.uniform(0.0, 0.3, size=(n_plans, 1)).astype(np.float32))
+        th = np.concatenate(lead + [th], axis=1)
     return th
 
 
+_POS = dict(ctrl=dict(controller_type="position"))
 _REPLAN25 = dict(replanning_schedule=lambda p, v, o, a, t: t % 25 == 0, max_planning_times=4)
 # file name, env id, seeds, black-box kwargs[, env constructor overrides]
 BB_CASES = [
@@ -216,19 +251,29 @@ BB_CASES = [
      dict(learn_sub_trajectories=True, condition_on_desired=True)),
     ("bb_viapoint_dmp_subtraj", "fancy_DMP/ViaPointReacher-v0", list(range(6)), dict(learn_sub_trajectories=True)),
     ("bb_holereacher_promp_subtraj", "fancy_ProMP/HoleReacher-v0", list(range(6)), dict(learn_sub_trajectories=True)),
+    # position controller (pos_controller.py:8-9: the action is the desired POSITION) through every kernel variant that can
+    # carry it: run-time K with the registry's 5 basis functions and with 7, the trajectory-from-HBM variant (a learned tau
+    # per env), DMP, and the torque-controlled env
+    ("bb_holereacher_promp_posctrl", "fancy_ProMP/HoleReacher-v0", list(range(8)), {}, {}, _POS),
+    ("bb_holereacher_promp_posctrl_k7", "fancy_ProMP/HoleReacher-v0", list(range(6)), {}, {}, dict(_POS, basis=dict(num_basis=7))),
+    ("bb_holereacher_promp_posctrl_tau", "fancy_ProMP/HoleReacher-v0", list(range(6)), {}, {},
+     dict(_POS, phase=dict(learn_tau=True, learn_delay=True))),
+    ("bb_viapoint_dmp_posctrl", "fancy_DMP/ViaPointReacher-v0", list(range(6)), {}, {}, _POS),
+    ("bb_simplereacher_prodmp_posctrl", "fancy_ProDMP/SimpleReacher-v0", list(range(6)), {}, {}, _POS),
 ]
 
 
 def bb_case(case):
-    """(file name, env id, seeds, black-box kwargs, env overrides)"""
-    return (*case, {}) if len(case) == 4 else case
+    """(file name, env id, seeds, black-box kwargs, env overrides, MP section overrides)"""
+    case = tuple(case)
+    return case + ({},) * (6 - len(case))
 
 
 T_PAD = 200      # rows the planned trajectories of sub-trajectory cases are zero-padded to (max_episode_steps)
 
 
 def gen_bb(ns, only=None):
-    for fname, env_id, seeds, bbk, env_over in map(bb_case, BB_CASES):
+    for fname, env_id, seeds, bbk, env_over, mp_over in map(bb_case, BB_CASES):
         if only and only not in fname:
             continue
         sub_traj = bool(bbk.get("learn_sub_trajectories"))
@@ -236,9 +281,9 @@ def gen_bb(ns, only=None):
         rec = {k: [] for k in ("obs0", "params", "positions", "velocities", "step_obs", "step_rewards",
                                "ret", "length", "terminated", "truncated", "obs", "n_calls", "n_points")}
         for s in seeds:
-            bb = build_reference_bb(ns, env_id, "shipped", bbk, env_over)
+            bb = build_reference_bb(ns, env_id, "shipped", bbk, env_over, mp_over)
             ob0, _ = bb.reset(seed=s)
-            th = params_for(env_id, s, n_plans, sub_traj)
+            th = params_for(env_id, s, n_plans, sub_traj, mp_over)
             per = {k: [] for k in rec if k not in ("obs0", "params", "n_calls")}
             calls = 0
             for i in range(n_plans):
@@ -272,7 +317,7 @@ def gen_bb(ns, only=None):
         np.savez_compressed(os.path.join(HERE, fname + ".npz"), **out)
 
         # ---- pin the oracle's loop (same 'shipped' MP) against the reference's BlackBoxWrapper ----
-        orc = make_oracle(env_id, mode="shipped", verbose=2, mp_overrides={"env": env_over}, **bbk)
+        orc = make_oracle(env_id, mode="shipped", verbose=2, mp_overrides=dict(mp_over, env=env_over), **bbk)
         ob0 = orc.reset(seeds=seeds)
         assert np.array_equal(ob0, out["obs0"]), fname
         alive = np.ones(len(seeds), bool)

@@ -21,9 +21,21 @@ def _setup(env_id, B, seed=0):
     D = tg._num_local_params
     rng = np.random.default_rng(seed)
     L = np.tril(0.1 * rng.standard_normal((B, D, D))) + 0.5 * np.eye(D)        # BASELINE config 4
-    tb = tg.tables()
-    basis = tb.tab_a if env_id.startswith("fancy_ProMP") else tb.tab_a[:, 2:]
-    return env, tg, L.astype(np.float32), np.asarray(basis, dtype=np.float64)
+    return env, tg, L.astype(np.float32), _oracle_basis(env_id, D)
+
+
+def _oracle_basis(env_id, D):
+    """Psi's diagonal block [T, Kc] from the ORACLE (float64 definition, oracle/mp.py), not from the product's own tables:
+    ProMP weights_scale * Phi (learnable columns), ProDMP the bracketed H = [H_w | H_g] of App. B.7"""
+    orc = make_oracle(env_id, mode="gold")
+    orc.reset(seeds=[0])
+    otg = orc.traj_gen
+    otg.set_params(np.zeros((1, D)))
+    otg.set_initial_conditions(np.array(0.0), orc.env.current_pos, orc.env.current_vel)
+    otg.set_duration(2.0, 0.01)
+    if env_id.startswith("fancy_ProMP"):
+        return np.asarray(otg._scaled_basis_learnable(), dtype=np.float64)
+    return np.asarray(otg.tables()[0], dtype=np.float64)
 
 
 @pytest.mark.parametrize("env_id,B", [("fancy_ProMP/HoleReacher-v0", 3), ("fancy_ProDMP/SimpleReacher-v0", 17),

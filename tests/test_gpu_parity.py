@@ -15,7 +15,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle.blackbox import make_oracle  # noqa: E402
-from tests.golden.make_golden import BB_CASES, bb_case, n_params_of  # noqa: E402
+from tests.golden.make_golden import BB_CASES, bb_case, mp_config_override_of, n_params_of  # noqa: E402
 
 TIE_EPS = 1e-5
 
@@ -75,18 +75,34 @@ def test_trajgen_empty_and_single():
 # --------------------------------------------------------------------------------------------
 # fused rollout against the golden vectors produced from the reference's own files
 # --------------------------------------------------------------------------------------------
+# Tolerances of the golden comparison = 2 x the maxima measured on the B200 over all cases (profiles/r2_golden_errors.json,
+# written by this test; DESIGN.md §2 "measured parity").  The goldens carry the reference's float32 MP in BLAS order
+# ('shipped'); the CUDA path evaluates float64-built tables with an FMA chain ('mirror').  Velocity-like entries inherit the
+# reference's own float32 finite-difference noise ~ 2^-24 |pos| / dt (the float64 definition is as far from the goldens
+# as the CUDA path is), which is why they are the widest.
+GOLDEN_TOL = dict(obs0=1e-6, ret=1e-5, obs=5e-5, positions=1e-5, velocities=3e-5, step_obs=5e-5, step_obs_vel=3e-4,
+                  step_rewards=2e-4)
+_golden_err = {}
+
+
 @pytest.mark.parametrize("case", BB_CASES, ids=[c[0] for c in BB_CASES])
 def test_rollout_matches_reference_goldens(case, golden_dir):
     fancy_gym = _fg()
-    fname, env_id, seeds, bbk, env_over = bb_case(case)
+    fname, env_id, seeds, bbk, env_over, mp_over = bb_case(case)
     g = np.load(os.path.join(golden_dir, fname + ".npz"))
-    override = {"black_box_kwargs": dict(bbk, verbose=2)}
+    override = mp_config_override_of(env_id, mp_over, dict(bbk, verbose=2))
     B = len(seeds)
     env = fancy_gym.make(env_id, num_envs=B, device="cuda:0", mp_config_override=override, **env_over)
     obs0, _ = env.reset(seed=np.array(seeds), options={"as_numpy": True})
-    assert np.allclose(obs0, g["obs0"], rtol=0, atol=1e-6)
+    err = dict.fromkeys(GOLDEN_TOL, 0.0)
+
+    def track(key, value):
+        err[key] = max(err[key], float(np.max(value, initial=0.0)))
+
+    track("obs0", np.abs(obs0 - g["obs0"]))
     n_plans = g["params"].shape[1]
     last_obs = {}
+    nl = env.unwrapped.n_links
     for i in range(n_plans):
         live = i < g["n_calls"]
         if not live.any():
@@ -100,30 +116,35 @@ def test_rollout_matches_reference_goldens(case, golden_dir):
             assert bool(te[b]) == bool(g["terminated"][b, i]) and bool(tr[b]) == bool(g["truncated"][b, i])
             r_ref = g["ret"][b, i]
             if np.isfinite(r_ref):
-                assert rel_err(ret[b], r_ref).max() < 1e-5, (fname, b, i, ret[b], r_ref)
+                track("ret", rel_err(ret[b], r_ref))
             else:
                 assert ret[b] == r_ref
-            # the goldens carry the 'shipped' float32 MP (BLAS-order einsum); velocity-like entries inherit the
-            # reference's own finite-difference noise ~ 2^-23 |pos| / dt ~ 3e-5
-            oscale = np.maximum(1.0, np.abs(g["obs"][b, i]))
-            assert (np.abs(obs[b] - g["obs"][b, i]) <= 5e-5 * oscale).all(), (fname, b, i, obs[b], g["obs"][b, i])
+            track("obs", np.abs(obs[b] - g["obs"][b, i]) / np.maximum(1.0, np.abs(g["obs"][b, i])))
             # verbose=2 infos: the planned trajectory and the per-step observations / rewards of the reference's loop
             L = g["length"][b, i]
-            n = g["n_points"][b, i] if "n_points" in g.files else len(g["positions"][b, i])   # sub-trajectories: ragged plans
-            assert rel_err(info["positions"][b][:n], g["positions"][b, i][:n]).max() < 1e-5
+            n = g["n_points"][b, i]         # sub-trajectories: ragged plans
+            track("positions", rel_err(info["positions"][b][:n], g["positions"][b, i][:n]))
             vscale = max(1.0, np.abs(g["velocities"][b, i]).max())
-            assert rel_err(info["velocities"][b][:n], g["velocities"][b, i][:n], scale=vscale).max() < 3e-5
+            track("velocities", rel_err(info["velocities"][b][:n], g["velocities"][b, i][:n], scale=vscale))
             so, so_ref = info["step_observations"][b, :L], g["step_obs"][b, i, :L]
-            tol = np.full(so.shape[1], 5e-5)
-            n = env.unwrapped.n_links
-            tol[2 * n:3 * n] = 3e-4        # joint velocities: float32 finite differences of the trajectory (see above)
-            assert (np.abs(so - so_ref) <= tol * np.maximum(1.0, np.abs(so_ref))).all(), \
-                (fname, b, i, np.abs(so - so_ref).max(axis=0))
+            e = np.abs(so - so_ref) / np.maximum(1.0, np.abs(so_ref))
+            is_vel = np.zeros(so.shape[1], bool)
+            is_vel[2 * nl:3 * nl] = True       # joint velocities: float32 finite differences of the trajectory (see above)
+            track("step_obs", e[:, ~is_vel])
+            track("step_obs_vel", e[:, is_vel])
             sr, sr_ref = info["step_rewards"][b, :L], g["step_rewards"][b, i, :L]
             fin = np.isfinite(sr_ref)
             assert np.array_equal(sr[~fin], sr_ref[~fin])
             # per-step rewards are dominated by 5e-8 * sum(acc^2) with acc = dv/dt of float32 finite differences
-            assert (np.abs(sr[fin] - sr_ref[fin]) <= 1e-5 * np.maximum(1.0, np.abs(sr_ref[fin])) + 1e-4 * np.abs(sr_ref[fin])).all(), (fname, b, i)
+            track("step_rewards", np.abs(sr[fin] - sr_ref[fin]) / np.maximum(1.0, np.abs(sr_ref[fin])))
+    _golden_err[fname] = err
+    os.makedirs("gpurun_out", exist_ok=True)
+    import json
+    with open(os.path.join("gpurun_out", "golden_errors.json"), "w") as f:
+        worst = {k: max(e[k] for e in _golden_err.values()) for k in GOLDEN_TOL}
+        json.dump({"tolerance": GOLDEN_TOL, "measured_max_over_cases": worst, "per_case": _golden_err}, f, indent=1)
+    for k, tol in GOLDEN_TOL.items():
+        assert err[k] <= tol, (fname, k, err[k], tol)
 
 
 # --------------------------------------------------------------------------------------------

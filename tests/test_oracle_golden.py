@@ -74,9 +74,9 @@ def test_survey_rollout_kats():
 
 @pytest.mark.parametrize("case", BB_CASES, ids=[c[0] for c in BB_CASES])
 def test_blackbox_loop_matches_reference_wrapper(case, golden_dir):
-    fname, env_id, seeds, bbk, env_over = bb_case(case)
+    fname, env_id, seeds, bbk, env_over, mp_over = bb_case(case)
     g = np.load(os.path.join(golden_dir, fname + ".npz"))
-    orc = make_oracle(env_id, mode="shipped", verbose=2, mp_overrides={"env": env_over}, **bbk)
+    orc = make_oracle(env_id, mode="shipped", verbose=2, mp_overrides=dict(mp_over, env=env_over), **bbk)
     ob0 = orc.reset(seeds=seeds)
     assert np.array_equal(ob0, g["obs0"])
     n_plans = g["params"].shape[1]
