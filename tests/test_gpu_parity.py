@@ -80,8 +80,10 @@ def test_trajgen_empty_and_single():
 # ('shipped'); the CUDA path evaluates float64-built tables with an FMA chain ('mirror').  Velocity-like entries inherit the
 # reference's own float32 finite-difference noise ~ 2^-24 |pos| / dt (the float64 definition is as far from the goldens
 # as the CUDA path is), which is why they are the widest.
-GOLDEN_TOL = dict(obs0=1e-6, ret=1e-5, obs=5e-5, positions=1e-5, velocities=3e-5, step_obs=5e-5, step_obs_vel=3e-4,
-                  step_rewards=2e-4)
+# measured maxima (B200, 28 cases): obs0 0, ret 1.05e-6, obs 2.4e-5, positions 2.0e-6, velocities 1.4e-5, step_obs 2.3e-6,
+# step_obs_vel 1.2e-4, step_rewards 4.3e-6
+GOLDEN_TOL = dict(obs0=1e-6, ret=2.2e-6, obs=4.8e-5, positions=4.1e-6, velocities=2.9e-5, step_obs=4.6e-6, step_obs_vel=2.4e-4,
+                  step_rewards=8.7e-6)
 _golden_err = {}
 
 
