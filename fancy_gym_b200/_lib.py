@@ -10,6 +10,7 @@ import os
 
 FG_MAX_DOF = 8
 FG_MAX_OBS = 40
+FG_MAX_PLANS = 32
 
 # enums (include/fancy_gym_b200.h)
 ENV_HOLE_REACHER, ENV_VIAPOINT_REACHER, ENV_SIMPLE_REACHER, ENV_TOY = 0, 1, 2, 3
@@ -46,6 +47,7 @@ class FgRolloutIO(C.Structure):
         ("use_cond", C.c_int32), ("write_cond", C.c_int32),
         ("ret", C.c_void_p), ("length", C.c_void_p), ("flags", C.c_void_p), ("obs", C.c_void_p), ("info", C.c_void_p),
         ("dbg_actions", C.c_void_p), ("dbg_obs", C.c_void_p), ("dbg_rewards", C.c_void_p), ("flag_bytes", C.c_void_p), ("seg_steps_env", C.c_void_p), ("prev_obs", C.c_void_p), ("prev_info", C.c_void_p), ("keep_state", C.c_int32),
+        ("n_plans", C.c_int32), ("plan_T", C.c_int32), ("plan_seg", C.c_int32 * FG_MAX_PLANS), ("plan_row0", C.c_int32 * FG_MAX_PLANS),
     ]
 
 
@@ -129,7 +131,7 @@ def _load():
 
 
 lib = _load()
-assert lib.fg_abi_version() == 1, "ABI version mismatch between fancy_gym_b200/_lib.py and the shared library"
+assert lib.fg_abi_version() == 2, "ABI version mismatch between fancy_gym_b200/_lib.py and the shared library"
 
 
 def check(status: int):

@@ -171,6 +171,19 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
   if (B == 0) return FG_OK;
   if (seg_steps < 1 || seg_steps > h->cfg.n_steps)
     return fail(FG_ERR_INVALID, "fg_rollout: seg_steps %d outside 1..%d", seg_steps, h->cfg.n_steps);
+  if (io->n_plans > 1) {       // plans looped inside the launch: the handle's tables hold every plan's rows
+    if (io->n_plans > FG_MAX_PLANS) return fail(FG_ERR_INVALID, "fg_rollout: n_plans %d > FG_MAX_PLANS", io->n_plans);
+    if (h->cfg.mp_kind == FG_MP_TRAJ || io->seg_steps_env || io->dbg_actions || io->dbg_obs || io->dbg_rewards)
+      return fail(FG_ERR_UNSUPPORTED, "fg_rollout: n_plans > 1 needs a table-driven MP and no per-step / per-env-length buffers");
+    if (io->plan_T < 2) return fail(FG_ERR_INVALID, "fg_rollout: plan_T %d < 2", io->plan_T);
+    for (int j = 0; j < io->n_plans; ++j) {
+      const int look = (h->cfg.mp_kind == FG_MP_PROMP && io->plan_seg[j] < io->plan_T) ? 1 : 0;   // ProMP reads row t + 1
+      if (io->plan_seg[j] < 1 || io->plan_seg[j] > io->plan_T || io->plan_row0[j] < 0 ||
+          io->plan_row0[j] + io->plan_seg[j] + look > h->cfg.n_steps)
+        return fail(FG_ERR_INVALID, "fg_rollout: plan %d (rows %d + %d steps) does not fit the handle's %d table rows", j,
+                    io->plan_row0[j], io->plan_seg[j], h->cfg.n_steps);
+    }
+  }
   const bool need_state = h->cfg.env_kind != FG_ENV_TOY;
   if ((need_state && (!io->q || !io->v || !io->ctx)) || !io->steps || !io->done || !io->ret || !io->length ||
       !io->flags || !io->obs || !io->info)

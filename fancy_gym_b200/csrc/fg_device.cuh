@@ -158,14 +158,12 @@ __device__ __noinline__ bool self_hits_accurate(const Angles<N> a) {
   return self_hits<N, true>(a.th, zero, zero, unused);
 }
 
+// any(q > pi) or any(q < -pi) (base_reacher.py:111): |q| > pi as an unsigned compare of the sign-stripped bit patterns
+// (non-negative doubles order like integers).  Fast screen on the HIGH words only: non-negative float patterns order like the
+// integers they are, so the largest sign-stripped high word is one FMNMX(3) chain with |.| modifiers; only when it reaches pi's
+// high word (|q| within 2^-20 of pi or beyond: rare) are the full 64-bit patterns compared.
 template <int N>
-__device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N], const float (&cs)[N],
-                                               const float (&sn)[N]) {
-  // any(q > pi) or any(q < -pi): |q| > pi as an unsigned compare of the sign-stripped bit patterns (non-negative doubles
-  // order like integers) — two integer compares per joint instead of the double-precision max chain ptxas builds
-  // Fast screen on the HIGH words only: non-negative float patterns order like the integers they are, so the largest
-  // sign-stripped high word is one FMNMX(3) chain with |.| modifiers; only when it reaches pi's high word (|q| within 2^-20
-  // of pi or beyond: rare) are the full 64-bit patterns compared.
+__device__ __forceinline__ bool joint_limits(const double (&q)[N]) {
   bool lim = false;
   constexpr unsigned long long kPiBits = 0x400921FB54442D18ULL;
   float hi_max = 0.f;
@@ -176,19 +174,49 @@ __device__ __forceinline__ bool self_collision(const double (&q)[N], const doubl
     for (int i = 0; i < N; ++i)
       lim |= ((unsigned long long)__double_as_longlong(q[i]) & 0x7FFFFFFFFFFFFFFFULL) > kPiBits;
   }
+  return lim;
+}
+
+// Can two non-adjacent links touch at all?  If link i meets link j (j >= i + 2) at a point P, then P, joint i+1, ..., joint j is
+// a closed polygon; the exterior angles of a closed polygon sum to at least 2 pi in absolute value and the one at P is below
+// pi, so the joints between the two links turn by MORE than pi: sum_{l=i+1..j} |q_l| > pi (the relative joint angles are the
+// exterior angles).  Hence, while sum_{l=1..N-1} |q_l| <= 3.0 (< pi, with room for the float32 sum), no pair of links intersects
+// and every orientation test of the reference comes out "no hit"; the whole pair evaluation (18 orientation values for 5
+// links, ~95 instructions) is skipped.  At sigma = 0.25 (BASELINE config 2) this holds on 99.8 % of the warp-steps.
+constexpr float kTurnScreen = 3.0f;
+template <int N>
+__device__ __forceinline__ bool may_self_intersect(const double (&q)[N]) {
   if constexpr (N < 3) {
-    return lim;
+    return false;
   } else {
-    float min_abs;
-    bool hit = self_hits<N, false>(th, cs, sn, min_abs);
-    if (min_abs <= 8e-6f) {
-      Angles<N> a;
+    float turn = 0.f;
 #pragma unroll
-      for (int i = 0; i < N; ++i) a.th[i] = th[i];
-      hit = self_hits_accurate<N>(a);
-    }
-    return lim | hit;
+    for (int i = 1; i < N; ++i) turn += fabsf((float)q[i]);
+    return !(turn <= kTurnScreen);        // (a NaN angle takes the full evaluation)
   }
+}
+
+// the pair tests themselves: orientation values from the FK sin / cos first; the accurate evaluation only if one of them is
+// within 8e-6 of zero (nearly collinear links)
+template <int N>
+__device__ __forceinline__ bool links_intersect(const double (&th)[N], const float (&cs)[N], const float (&sn)[N]) {
+  float min_abs;
+  bool hit = self_hits<N, false>(th, cs, sn, min_abs);
+  if (min_abs <= 8e-6f) {
+    Angles<N> a;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.th[i] = th[i];
+    hit = self_hits_accurate<N>(a);
+  }
+  return hit;
+}
+
+template <int N>
+__device__ __forceinline__ bool self_collision(const double (&q)[N], const double (&th)[N], const float (&cs)[N],
+                                               const float (&sn)[N]) {
+  bool hit = joint_limits<N>(q);
+  if (may_self_intersect<N>(q)) hit |= links_intersect<N>(th, cs, sn);
+  return hit;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -237,9 +265,47 @@ __device__ __forceinline__ bool overlap3(Span a, Span b, Span c) {
   return max(max(a.lo, b.lo), c.lo) < min(min(a.hi, b.hi), c.hi);
 }
 
-// (out of line: up to N calls per step share ONE copy of the six unrolled searches — the fused kernel's loop body
-//  otherwise exceeds the instruction cache; measured "no_instruction" stalls, profiles/README.md)
+// Transition index by ESTIMATE + exact fix-up: the walked sequence g(i) = fma(k, s(i), off) is non-decreasing, so the
+// count of samples below tau is the unique i with g(i-1) below and g(i) not below.  Solving the line for tau gives i to
+// within a sample; the two fix-up loops then move it until the SAME float32 expressions the literal evaluation uses bracket
+// it — whatever the estimate was (k == 0, inf, NaN included: they only cost iterations), the result is the binary search's.
+// ~25 instructions instead of ~60; n_le (samples <= tau) continues from n_lt (samples < tau): one more evaluation.
+__device__ __forceinline__ float walked(const float* __restrict__ s_m, float k, float off, int i, bool rev) {
+  return fmaf(k, s_m[rev ? (kLinePoints - 1 - i) : i], off);
+}
+__device__ __forceinline__ int count_lt_est(const float* __restrict__ s_m, float k, float r99k, float off, float tau, bool rev) {
+  float e = (tau - off) * r99k;                        // sample coordinate where the line crosses tau
+  e = rev ? (float)(kLinePoints - 1) - e : e;
+  int i = (int)fminf(fmaxf(e, -1.0f), (float)kLinePoints) + 1;      // (fmaxf drops a NaN estimate)
+  i = min(max(i, 0), kLinePoints);
+  while (i > 0 && !(walked(s_m, k, off, i - 1, rev) < tau)) --i;
+  while (i < kLinePoints && walked(s_m, k, off, i, rev) < tau) ++i;
+  return i;
+}
+__device__ __forceinline__ int count_le_from(const float* __restrict__ s_m, float k, float off, float tau, bool rev, int n_lt) {
+  int i = n_lt;                                        // samples == tau follow the ones below it
+  while (i < kLinePoints && walked(s_m, k, off, i, rev) <= tau) ++i;
+  return i;
+}
+
+// (out of line: up to N calls per step share ONE copy of the searches — the fused kernel's loop body otherwise exceeds the
+//  instruction cache; measured "no_instruction" stalls, profiles/README.md)
 static __device__ __noinline__ bool link_wall_search(const float* __restrict__ s_m, float c, float s, float X, float Y, const Hole h) {
+  const bool rx = c < 0.f, ry = s < 0.f;
+  const float rc = __fdividef((float)(kLinePoints - 1), c), rs = __fdividef((float)(kLinePoints - 1), s);   // estimates only
+  const int n_lt_l = count_lt_est(s_m, c, rc, X, h.xl, rx), n_le_l = count_le_from(s_m, c, X, h.xl, rx, n_lt_l);
+  const int n_lt_r = count_lt_est(s_m, c, rc, X, h.xr, rx), n_le_r = count_le_from(s_m, c, X, h.xr, rx, n_lt_r);
+  const Span A = span_below(n_lt_l, rx);           // x <  xl
+  const Span Bx = span_above(n_le_r, rx);          // x >  xr
+  const Span Gl = span_above(n_le_l, rx);          // x >  xl
+  const Span Lr = span_below(n_lt_r, rx);          // x <  xr
+  const Span C = span_below(count_lt_est(s_m, s, rs, Y, 0.f, ry), ry);           // y <  0
+  const Span D = span_below(count_lt_est(s_m, s, rs, Y, h.nd, ry), ry);          // y < -depth
+  return overlap(A, C) | overlap(Bx, C) | overlap3(Gl, Lr, D);
+}
+
+// the round-1 formulation (six 7-step binary searches), kept as wall_mode 3 for A/B runs
+static __device__ __noinline__ bool link_wall_bisect(const float* __restrict__ s_m, float c, float s, float X, float Y, const Hole h) {
   const bool rx = c < 0.f, ry = s < 0.f;
   const Span A = span_below(count_below<false>(s_m, c, X, h.xl, rx), rx);          // x <  xl
   const Span Bx = span_above(count_below<true>(s_m, c, X, h.xr, rx), rx);          // x >  xr
@@ -282,7 +348,8 @@ __device__ __forceinline__ bool wall_collision(const float* __restrict__ s_m, co
     for (int i = 0; i < N; ++i) {
       if (wall_mode == 2 || fminf(Ys[i], Ys[i + 1]) < ythr)
         hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], X, Ys[i], h)
-                                : link_wall_brute(s_m, cs[i], sn[i], X, Ys[i], h);
+               : (wall_mode == 3) ? link_wall_bisect(s_m, cs[i], sn[i], X, Ys[i], h)
+                                  : link_wall_brute(s_m, cs[i], sn[i], X, Ys[i], h);
       X = fmaf(cs[i], 1.0f, X);
     }
   }

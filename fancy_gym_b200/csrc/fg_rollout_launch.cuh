@@ -9,9 +9,10 @@ template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
 cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
                       int max_smem_optin, const char** why) {
   const int pw = N * weight_slots(MP, c.K);
-  const size_t smem = sizeof(float) * rollout_smem_floats(c.T, c.cols_a, c.rows_b, c.cols_b, pw, kRolloutThreads);
+  const size_t smem = rollout_smem_bytes(c.T, c.cols_a, c.rows_b, c.cols_b, pw, SlotLayout<ENV, MP, MOTOR, N, KC>::WORDS,
+                                         kRolloutThreads);
   if (smem > (size_t)max_smem_optin) {
-    *why = "tables + per-thread weights exceed the shared memory of one SM (reduce n_steps or n_basis)";
+    *why = "tables + per-env weights and state exceed the shared memory of one SM (reduce n_steps or n_basis)";
     return cudaSuccess;
   }
   auto kern = k_rollout<ENV, MP, MOTOR, N, KC, DBG>;
@@ -20,7 +21,13 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
     if (e != cudaSuccess) return e;
   }
   const long long blocks = (B + kRolloutThreads - 1) / kRolloutThreads;
-  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, io, B, seg_steps);
+  fg_rollout_io iok = io;
+  if (iok.n_plans <= 1) {      // one plan: the whole table is that plan
+    iok.n_plans = 1;
+    iok.plan_T = c.T;
+    iok.plan_row0[0] = 0;
+  }
+  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps);
   return cudaGetLastError();
 }
 

@@ -30,9 +30,10 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 1
+#define FG_ABI_VERSION 2
 #define FG_MAX_DOF 8      /* links / action dimensions handled in registers */
 #define FG_MAX_OBS 40     /* 3*FG_MAX_DOF + 5 (+1 time-aware column) */
+#define FG_MAX_PLANS 32   /* plans of one episode that one fg_rollout launch can loop over */
 
 typedef enum fg_status {
   FG_OK = 0,
@@ -100,8 +101,9 @@ typedef struct fg_config {
   double collision_penalty;
   int32_t rew_fct;             /* hole reacher (hole_reacher.py:48-58): 0 = "simple" (hr_simple_reward.py),
                                   1 = "vel_acc" (hr_dist_vel_acc_reward.py), 2 = "unbounded" (hr_unbounded_reward.py) */
-  int32_t wall_mode;           /* 0 = exact interval search over the 100 samples/link (default),
-                                  1 = literal evaluation of all 100 samples/link (hole_reacher.py:148-179) */
+  int32_t wall_mode;           /* 0 = exact transition search over the 100 samples/link: closed-form estimate + fix-up (default),
+                                  1 = literal evaluation of all 100 samples/link (hole_reacher.py:148-179), 2 = the same without
+                                  skipping links that stay above ground, 3 = transition search by bisection (round 1) */
   int32_t time_aware;          /* append elapsed/max_episode_steps to obs (utils/wrappers.py:49-63) */
 
   /* observation compaction: obs_out[:, j] = full_step_obs[:, obs_index[j]] (context mask,
@@ -161,6 +163,18 @@ typedef struct fg_rollout_io {
   const double* prev_info; /* [B, 4] or NULL      episode ended in an earlier call (they keep reporting their last values)   */
   int32_t keep_state;      /* 1: q / v / steps / done are read but NOT written back: the batch can be evaluated again from the
                               same start state with other parameters (population-based search on one context) */
+  /* Re-planning inside ONE launch (black_box_wrapper.py:197-203 with a schedule that depends on the step counter only — every
+   * schedule in the reference has the form t % k == 0): n_plans > 1 makes `params` [B, n_plans, P]; plan j executes
+   * plan_seg[j] steps (the schedule's break points, evaluated by the caller) and reads rows plan_row0[j] + t of the handle's
+   * tables, which then hold the rows of all plans one after the other (each plan planned from its own start time, plus one
+   * look-ahead row); plan_T = points of one plan.  The boundary condition of plan j + 1 is the env's state at the break or,
+   * with write_cond != 0 (condition_on_desired), the desired state of the break step.  Every output buffer then holds
+   * n_plans blocks ([n_plans, B, ...]: what the j-th step() call of the reference returns); an env whose episode ends in
+   * plan j reports 0 steps and its last observation for the plans after it.  0 / 1: one plan (the seg_steps argument). */
+  int32_t n_plans;
+  int32_t plan_T;
+  int32_t plan_seg[FG_MAX_PLANS];
+  int32_t plan_row0[FG_MAX_PLANS];
 } fg_rollout_io;
 
 /* Episode reset of the classic_control reachers on the device (replaces the host-side samplers

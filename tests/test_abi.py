@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} is declared in the header but not exported by {_lib.LIB_PATH}"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names
-    assert _lib.lib.fg_abi_version() == 1
+    assert _lib.lib.fg_abi_version() == 2
 
 
 def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):

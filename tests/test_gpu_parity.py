@@ -211,14 +211,14 @@ def _run(env, params, seed):
 
 
 def test_wall_modes_agree_at_full_size():
-    """The interval-search wall test (mode 0) must give exactly the flags of the literal 100-samples-per-link
-    evaluation (mode 1: with the exact skip of links above ground, mode 2: no skipping at all)."""
+    """The transition-search wall test (mode 0: estimate + fix-up, mode 3: bisection) must give exactly the flags of the
+    literal 100-samples-per-link evaluation (mode 1: with the exact skip of links above ground, mode 2: no skipping at all)."""
     fancy_gym = _fg()
     B = 65536
     gen = torch.Generator(device="cuda:0").manual_seed(0)
     params = torch.randn(B, 25, generator=gen, device="cuda:0")
     outs = []
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device="cuda:0", context_sampler="device",
                              mp_config_override={"black_box_kwargs": {"wall_mode": mode}})
         outs.append(_run(env, params, 7))
