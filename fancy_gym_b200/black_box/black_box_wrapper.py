@@ -25,6 +25,20 @@ from .controller import BaseController
 from .raw_interface_wrapper import RawInterfaceWrapper
 
 
+def _masked_median(rewards: torch.Tensor, length: torch.Tensor) -> torch.Tensor:
+    """np.median over the executed steps of every env, on the device: rewards [B, T] float64, length [B].  Sort with the
+    steps past the episode's end pushed to +inf, then average the two middle elements (numpy's definition)."""
+    B, T = rewards.shape
+    t = torch.arange(T, device=rewards.device)[None, :]
+    r = torch.where(t < length[:, None], rewards, torch.full_like(rewards, float("inf")))
+    r, _ = torch.sort(r, dim=1)
+    L = length.clamp(min=1).to(torch.int64)
+    lo, hi = (L - 1) // 2, L // 2
+    a, b = r.gather(1, lo[:, None])[:, 0], r.gather(1, hi[:, None])[:, 0]
+    med = torch.where(a == b, a, (a + b) / 2)         # (equal -inf / +inf values must not turn into nan)
+    return torch.where(length > 0, med, torch.zeros_like(med))
+
+
 class BlackBoxWrapper(Wrapper):
 
     def __init__(self,
@@ -39,7 +53,9 @@ class BlackBoxWrapper(Wrapper):
                  max_planning_times: int = np.inf,
                  condition_on_desired: bool = False,
                  wall_mode: int = 0,
-                 result_sets: int = 2):
+                 result_sets: int = 2,
+                 schedule_host_callback: bool = False,
+                 max_cached_plans: int = 8):
         super().__init__(env)
         self.duration = duration
         self.learn_sub_trajectories = learn_sub_trajectories
@@ -71,6 +87,11 @@ class BlackBoxWrapper(Wrapper):
         self.max_planning_times = max_planning_times
         self.plan_steps = 0
         self.wall_mode = int(wall_mode)
+        # A replanning_schedule that inspects pos / vel / obs / action cannot run inside the fused kernel.  On request it is
+        # evaluated on the host from the recorded per-step state of a trial rollout (single env only; see _host_schedule_steps).
+        self.schedule_host_callback = bool(schedule_host_callback)
+        self._breaks = None
+        self.max_cached_plans = int(max_cached_plans)
         self._interface_checked = False
         self._traj_buf = None
         self._fast_reset = self._can_fast_reset()
@@ -189,6 +210,7 @@ class BlackBoxWrapper(Wrapper):
         key = ("traj", tg.n_steps) if from_trajectory else tg.table_key()
         h = self._handles.get(key)
         if h is not None:
+            self._handles[key] = self._handles.pop(key)       # most recently used last
             return h
         if from_trajectory:
             from ..mp.mp import MPTables
@@ -196,6 +218,20 @@ class BlackBoxWrapper(Wrapper):
                           tab_b=np.zeros(1, np.float32))
         else:
             tb = tg.tables()
+        hp = self._create_handle(tb)
+        self._remember_handle(key, hp)
+        return hp
+
+    def _remember_handle(self, key, hp):
+        """bounded cache: a learned scalar tau / delay gives a new table key almost every episode; the least recently used
+        handle is destroyed (its launches are stream ordered before the destroy: cudaFree waits)"""
+        self._handles[key] = hp
+        while len(self._handles) > self.max_cached_plans:
+            old_key = next(iter(self._handles))
+            _lib.lib.fg_destroy(self._handles.pop(old_key))
+
+    def _create_handle(self, tb):
+        base = self._base
         cfg = _lib.FgConfig()
         cfg.struct_size = C.sizeof(_lib.FgConfig)
         cfg.env_kind, cfg.mp_kind = base.env_kind, tb.mp_kind
@@ -220,25 +256,59 @@ class BlackBoxWrapper(Wrapper):
         cfg.tab_a, cfg.tab_b = ta.ctypes.data, tbb.ctypes.data
         hp = C.c_void_p()
         _lib.check(_lib.lib.fg_create(C.byref(cfg), self.device.index or 0, C.byref(hp)))
-        self._handles[key] = hp
         return hp
 
     # ---- replanning: how many steps does this plan execute? (black_box_wrapper.py:197) -----------
+    def _break_points(self):
+        """Steps t (1-based, counted over the episode) at which the schedule fires, evaluated ONCE with the step counter
+        only — every schedule in the reference and its tests has the form `t % k == 0`.  None if the
+        schedule needs the state (it raised on the None arguments)."""
+        if self._breaks is None:
+            n = int(self.env.spec.max_episode_steps)
+            try:
+                self._breaks = [t for t in range(1, n + 1) if self.replanning_schedule(None, None, None, None, t)]
+            except Exception:      # noqa: BLE001  (whatever the callable does with None: it looks at the state)
+                self._breaks = False
+        return None if self._breaks is False else self._breaks
+
     def _segment_steps(self, n_steps: int):
-        """The schedule is evaluated on the host with the step counter only — every schedule in the
-        reference and its tests has the form `t % k == 0`.  A schedule that inspects pos / vel / obs /
-        action cannot be fused and raises."""
+        """(steps this plan executes, whether they end in a re-planning break) — black_box_wrapper.py:197."""
         if not self.do_replanning or not (self.plan_steps < self.max_planning_times):
             return n_steps, False
-        for t in range(n_steps):
-            try:
-                fire = self.replanning_schedule(None, None, None, None, t + 1 + self.current_traj_steps)
-            except TypeError as e:
-                raise NotImplementedError("replanning_schedule must depend on the step counter only "
-                                          "(it is evaluated on the host, outside the fused kernel)") from e
-            if fire:
-                return t + 1, True
+        breaks = self._break_points()
+        if breaks is None:
+            if not self.schedule_host_callback:
+                raise NotImplementedError("replanning_schedule must depend on the step counter only (it is evaluated on the host, "
+                                          "outside the fused kernel); pass black_box_kwargs={'schedule_host_callback': True} to "
+                                          "evaluate a state-dependent schedule on the host (single env)")
+            return None, True          # decided by _host_schedule_steps from a trial rollout
+        import bisect
+        i = bisect.bisect_right(breaks, self.current_traj_steps)
+        if i < len(breaks) and breaks[i] - self.current_traj_steps <= n_steps:
+            return breaks[i] - self.current_traj_steps, True
         return n_steps, False
+
+    def _host_schedule_steps(self, local, T):
+        """State-dependent schedule (fallback on request): the plan is rolled out once WITHOUT committing the state
+        (keep_state) with the per-step buffers of verbose >= 2 plus the per-step joint state, the schedule is called on the
+        host with (pos, vel, obs, action, t) exactly like black_box_wrapper.py:197, and the first firing step bounds the real
+        launch.  One env only: in a batch every env would break at its own step and leave the shared plan clock."""
+        if self.num_envs != 1:
+            raise NotImplementedError("schedule_host_callback is available for num_envs == 1")
+        n = self._base.n_links
+        dbg = dict(rewards=torch.zeros(1, T, dtype=torch.float64, device=self.device),
+                   actions=torch.zeros(1, T, n, dtype=torch.float64, device=self.device),
+                   obs=torch.zeros(1, T, self.env.observation_space.shape[0], dtype=torch.float32, device=self.device),
+                   state=torch.zeros(1, T, 2 * n, dtype=torch.float64, device=self.device))
+        self.launch(local, T, False, dbg, keep_state=True)
+        L = int(self._len[0])
+        st, ob, ac = dbg["state"][0].cpu().numpy(), dbg["obs"][0].cpu().numpy(), dbg["actions"][0].cpu().numpy()
+        self._out_i = (self._out_i - 1) % len(self._out_sets)      # the trial's result set is recycled by the real launch
+        self._bind_outputs()
+        for t in range(L):
+            if self.replanning_schedule(st[t, :n], st[t, n:], ob[t], ac[t], t + 1 + self.current_traj_steps):
+                return t + 1, True
+        return T, False
 
     # ---- the hot path ---------------------------------------------------------------------------
     def get_trajectory(self, action):
@@ -284,7 +354,8 @@ class BlackBoxWrapper(Wrapper):
         tg.set_initial_conditions(init_time, self._base.q, self._base.v)   # current_pos / current_vel (:110-111)
         tg.set_duration(duration, self.dt)
 
-    def launch(self, params, seg_steps=None, replan_break=False, dbg=None, state=None, keep_state=False):
+    def launch(self, params, seg_steps=None, replan_break=False, dbg=None, state=None, keep_state=False, trajectory=None,
+               seg_steps_env=None):
         """Enqueues ONE fused rollout (fg_rollout) for the current plan on the current CUDA stream and returns
         immediately; results land in the wrapper's device buffers (_ret, _len, _flags, _obs, _info).
         `params` [B, P_local] float32 on the device (phase parameters already stripped).
@@ -294,7 +365,11 @@ class BlackBoxWrapper(Wrapper):
         B = self.num_envs
         T = self.traj_gen.n_steps
         per_env_phase = not self.traj_gen.phase_gn.uniform()
-        if per_env_phase:
+        if trajectory is not None:
+            # the desired trajectory comes from the caller (an MPWrapper hook has seen / changed it): tracked from HBM
+            self._traj_buf = tuple(x.to(self.device, torch.float32).contiguous() for x in trajectory)
+            per_env_phase = True
+        elif per_env_phase:
             # learned tau / delay differ per env: fg_trajgen_phase evaluates the basis per env, the fused rollout then
             # tracks that trajectory from HBM (8 KB per env, far below its compute time)
             if self._traj_buf is None or self._traj_buf[0].shape[1] != T:
@@ -327,7 +402,9 @@ class BlackBoxWrapper(Wrapper):
         io.ret, io.length, io.flags = self._ret.data_ptr(), self._len.data_ptr(), self._flags.data_ptr()
         io.obs, io.info = self._obs.data_ptr(), self._info.data_ptr()
         io.flag_bytes = self._flag_bytes[0].data_ptr()
-        if per_env_phase and self.traj_gen.n_steps_env is not None:      # ragged sub-trajectories: per-env plan lengths
+        if seg_steps_env is not None:
+            io.seg_steps_env = seg_steps_env.data_ptr()
+        elif per_env_phase and self.traj_gen.n_steps_env is not None:      # ragged sub-trajectories: per-env plan lengths
             io.seg_steps_env = self.traj_gen.n_steps_env.data_ptr()
         if self.do_replanning or self.learn_sub_trajectories:      # frozen envs keep reporting their last observation / infos
             io.prev_obs, io.prev_info = self._prev_obs.data_ptr(), self._prev_info.data_ptr()
@@ -337,6 +414,8 @@ class BlackBoxWrapper(Wrapper):
                 io.dbg_actions = dbg["actions"].data_ptr()
             if "obs" in dbg:
                 io.dbg_obs = dbg["obs"].data_ptr()
+            if "state" in dbg:
+                io.dbg_state = dbg["state"].data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(T if seg_steps is None else seg_steps), C.c_void_p(stream)))
 
@@ -347,6 +426,7 @@ class BlackBoxWrapper(Wrapper):
         sub-trajectories), where a step's outcome is the next step's start."""
         if self.do_replanning or self.learn_sub_trajectories:
             raise NotImplementedError("evaluate() is defined for envs that plan once per episode")
+        self.traj_gen.reset()       # every candidate is a first plan: learned tau / delay apply (they finalize per plan otherwise)
         return self.step(action, _keep_state=True)
 
     def step(self, action, _keep_state: bool = False):
@@ -355,10 +435,22 @@ class BlackBoxWrapper(Wrapper):
         self._set_plan(params)
         local = self.traj_gen.params.contiguous()
         T = self.traj_gen.n_steps
-        if not _keep_state:
-            self.plan_steps += 1
-        seg, replan_break = self._segment_steps(T)
         B, n = self.num_envs, base.n_links
+        # ---- the env adaptor's trajectory hooks (black_box_wrapper.py:154-172), only when an MPWrapper overrides them ----
+        trajectory, valid = None, None
+        if self._hooks_overridden():
+            pos, vel = self._planned_trajectory(local)
+            pos, vel = self.env.set_episode_arguments(params, pos, vel)
+            valid, pos, vel = self.env.preprocessing_and_validity_callback(params, pos, vel, self.tau_bound, self.delay_bound)
+            trajectory = (pos, vel)
+            valid = torch.as_tensor(valid, device=self.device).to(torch.bool).expand(B).contiguous()
+            if bool(valid.all()):
+                valid = None
+        if not _keep_state and (valid is None or bool(valid.any())):
+            self.plan_steps += 1           # (the reference returns before counting the plan when the trajectory is invalid)
+        seg, replan_break = self._segment_steps(T)
+        if seg is None:
+            seg, replan_break = self._host_schedule_steps(local, T)
         dbg = None
         need_rewards = self.verbose >= 2 or self.reward_aggregation not in (np.sum, np.mean, sum)
         if need_rewards:
@@ -366,8 +458,13 @@ class BlackBoxWrapper(Wrapper):
             if self.verbose >= 2:
                 dbg["actions"] = torch.zeros(B, T, n, dtype=torch.float64, device=self.device)
                 dbg["obs"] = torch.zeros(B, T, self.env.observation_space.shape[0], dtype=torch.float32, device=self.device)
-        planned = self._planned_trajectory(local) if self.verbose >= 2 else None   # before the state moves on
-        self.launch(local, seg, replan_break, dbg, keep_state=_keep_state)
+        planned = (trajectory or self._planned_trajectory(local)) if self.verbose >= 2 else None   # before the state moves on
+        seg_env = None
+        if valid is not None:      # envs whose trajectory is invalid execute nothing (and report what invalid_traj_callback says)
+            seg_env = torch.where(valid, int(seg), 0).to(torch.int32)
+            if self.traj_gen.n_steps_env is not None:
+                seg_env = torch.minimum(seg_env, self.traj_gen.n_steps_env)
+        self.launch(local, seg, replan_break, dbg, keep_state=_keep_state, trajectory=trajectory, seg_steps_env=seg_env)
         if self.condition_on_desired and replan_break and not _keep_state:
             # the desired state is recorded on a BREAK only (black_box_wrapper.py:196-201): at a re-planning break every
             # live env breaks at the same step (the kernel wrote its row); a plan that simply runs out records nothing, and
@@ -390,7 +487,10 @@ class BlackBoxWrapper(Wrapper):
         elif base.env_kind == _lib.ENV_SIMPLE_REACHER:
             infos["reward_dist"] = self._info[:, 0]
             infos["reward_ctrl"] = self._info[:, 1]
-        if need_rewards and self.reward_aggregation not in (np.sum, np.mean, sum):
+        if need_rewards and self.reward_aggregation is np.median:
+            ret = _masked_median(dbg["rewards"], length)          # on the device
+        elif need_rewards and self.reward_aggregation not in (np.sum, np.mean, sum):
+            # an arbitrary callable: per-env host loop over the executed steps (the reference's call, env by env)
             r = dbg["rewards"].cpu().numpy()
             ln = length.cpu().numpy()
             ret = torch.as_tensor(np.array([self.reward_aggregation(r[b, :ln[b]]) if ln[b] else 0.0 for b in range(B)]),
@@ -402,7 +502,188 @@ class BlackBoxWrapper(Wrapper):
             infos["step_rewards"] = dbg["rewards"]
         infos["trajectory_length"] = length
         obs = self._obs
+        if valid is not None:
+            obs, ret, terminated, truncated, infos = self._merge_invalid(valid, params, trajectory, obs, ret, terminated, truncated, infos)
         return self._format(obs, ret, terminated, truncated, infos, as_numpy, scalar)
+
+    def _hooks_overridden(self) -> bool:
+        """does any wrapper between this one and the step env override a trajectory hook of RawInterfaceWrapper?"""
+        if getattr(self, "_hooks", None) is None:
+            names = ("set_episode_arguments", "preprocessing_and_validity_callback", "invalid_traj_callback")
+            layer, found = self.env, False
+            while layer is not None and not found:
+                found = any(getattr(type(layer), nm, None) not in (None, getattr(RawInterfaceWrapper, nm)) for nm in names)
+                layer = getattr(layer, "env", None)
+            self._hooks = found
+        return self._hooks
+
+    def _merge_invalid(self, valid, params, trajectory, obs, ret, terminated, truncated, infos):
+        """envs with an invalid trajectory return the tuple of invalid_traj_callback (black_box_wrapper.py:169-172; called with
+        the reference's six arguments) and their episode is marked over when the callback says so"""
+        c_obs, c_ret, c_te, c_tr, c_info = self.env.invalid_traj_callback(params, trajectory[0], trajectory[1],
+                                                                          self.return_context_observation, self.tau_bound,
+                                                                          self.delay_bound)
+        dev, B = self.device, self.num_envs
+        inv = ~valid
+
+        def bc(x, like):
+            x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, device=dev).to(like.dtype)
+            return x.expand_as(like) if x.dim() <= like.dim() and x.numel() in (1, like[0].numel(), like.numel()) else x
+
+        c_obs = torch.as_tensor(np.asarray(c_obs) if not torch.is_tensor(c_obs) else c_obs, device=dev).to(obs.dtype)
+        if c_obs.shape[-1] != obs.shape[-1]:
+            c_obs = self.observation(c_obs) if c_obs.shape[-1] == self.env.observation_space.shape[0] else c_obs[..., :1].expand(obs.shape[-1])
+        obs = torch.where(inv[:, None], c_obs.expand_as(obs), obs)
+        ret = torch.where(inv, bc(c_ret, ret), ret)
+        terminated = torch.where(inv, bc(c_te, terminated), terminated)
+        truncated = torch.where(inv, bc(c_tr, truncated), truncated)
+        self._base.done |= (inv & (terminated | truncated)).to(self._base.done.dtype)
+        infos = dict(infos, trajectory_valid=valid)
+        for k_, v_ in (c_info or {}).items():
+            infos.setdefault(k_, v_)
+        return obs, ret, terminated, truncated, infos
+
+    # ---- re-planning inside ONE launch ----------------------------------------------------------------------------
+    def plan_schedule(self, n_plans: int):
+        """[(first episode step, steps executed)] of the next `n_plans` plans from the current step on, following
+        black_box_wrapper.py:197: a plan ends at the next step the schedule fires on (while plan_steps < max_planning_times)
+        or runs its full duration"""
+        breaks = self._break_points()
+        if breaks is None:
+            raise NotImplementedError("the plans of a state-dependent replanning_schedule cannot be laid out in advance")
+        import bisect
+        T = int(round(self.duration / self.dt))
+        horizon = int(self.env.spec.max_episode_steps)
+        out, s0, done_plans = [], self.current_traj_steps, self.plan_steps
+        for j in range(n_plans):
+            if s0 >= horizon:
+                raise ValueError(f"only {j} plan(s) fit into the rest of the episode ({horizon} steps)")
+            seg = T
+            if done_plans + j + 1 < self.max_planning_times:
+                i = bisect.bisect_right(breaks, s0)
+                if i < len(breaks) and breaks[i] - s0 <= T:
+                    seg = breaks[i] - s0
+            out.append((s0, seg))
+            s0 += seg
+        return out
+
+    def _plans_fusable(self) -> bool:
+        tg = self.traj_gen
+        return (self.do_replanning and not self.learn_sub_trajectories and self._break_points() is not None
+                and self.verbose < 2 and self.reward_aggregation in (np.sum, np.mean, sum) and tg.phase_gn.num_params == 0
+                and tg.phase_gn.assume["dmp_init_on_first_grid_point"] and not self._hooks_overridden())
+
+    def _plans_handle(self, sched):
+        """handle whose tables hold the rows of every plan of `sched`, one after the other (fg_rollout_io.n_plans): plan j is
+        planned from its own start time init_time = start_j * dt and contributes its first seg_j + 1 rows (the extra one is the
+        look-ahead row of ProMP's finite difference)"""
+        tg = self.traj_gen
+        key = ("plans", tuple(sched), tg.phase_gn.scalar_tau(), tg.phase_gn.scalar_delay())
+        h = self._handles.get(key)
+        if h is not None:
+            self._handles[key] = self._handles.pop(key)
+            return h[0], h[1]
+        from ..mp.mp import MPTables
+        rows_a, rows_b, row0, r = [], [], [], 0
+        tb = None
+        for s0, seg in sched:
+            tg.set_initial_conditions(s0 * self.dt, self._base.q, self._base.v)
+            tg.set_duration(self.duration, self.dt)
+            tb = tg.tables()
+            n = seg + 1
+            a = np.zeros((n,) + tb.tab_a.shape[1:], np.float32)
+            m = min(n, tb.tab_a.shape[0])
+            a[:m] = tb.tab_a[:m]
+            b = np.ones((n,) + tb.tab_b.shape[1:], np.float32)
+            m = min(n, tb.tab_b.shape[0])
+            b[:m] = tb.tab_b[:m]
+            rows_a.append(a); rows_b.append(b); row0.append(r)
+            r += n
+        tab_a, tab_b = np.concatenate(rows_a), np.concatenate(rows_b)
+        if tb.mp_kind != _lib.MP_PRODMP:
+            tab_b = tab_b[:-1]           # ProMP / DMP: n_steps - 1 increments
+        allp = MPTables(mp_kind=tb.mp_kind, n_basis=tb.n_basis, n_steps=r, tab_a=tab_a, tab_b=tab_b, tau=tb.tau,
+                        dmp_alpha=tb.dmp_alpha, weights_scale=tb.weights_scale, goal_scale=tb.goal_scale,
+                        relative_goal=tb.relative_goal)
+        hp = self._create_handle(allp)
+        self._remember_handle(key, (hp, row0))
+        return hp, row0
+
+    def step_plans(self, actions):
+        """`n_plans` consecutive step() calls of a re-planning env as ONE fused launch: actions [B, n_plans, P] ->
+        (obs [n_plans, B, O], return [n_plans, B], terminated [n_plans, B], truncated [n_plans, B], infos of [n_plans, B, ...]).
+        Row j is exactly what the j-th step(actions[:, j]) would return (black_box_wrapper.py:150-217 called n_plans times:
+        the schedule's break points, max_planning_times, condition_on_desired and the per-plan boundary conditions are
+        followed inside the kernel); use it when the plans do not depend on the observations in between (open-loop
+        sequences, population-based search over plan sequences).  Falls back to a loop over step() where the plans cannot be
+        laid out in advance (state-dependent schedule, learned tau / delay, verbose >= 2, trajectory hooks)."""
+        a = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
+        if a.dim() == 2 and self.num_envs == 1:
+            a = a[None]
+        B, P = self.num_envs, self.action_space.shape[0]
+        if a.dim() != 3 or a.shape[0] != B or a.shape[2] != P:
+            raise ValueError(f"expected actions of shape [{B}, n_plans, {P}], got {tuple(a.shape)}")
+        n_plans = a.shape[1]
+        if n_plans > _lib.FG_MAX_PLANS or not self._plans_fusable():
+            outs = [self.step(a[:, j].to(self.device)) for j in range(n_plans)]
+            keys = outs[0][4].keys()
+            return (torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]), torch.stack([o[2] for o in outs]),
+                    torch.stack([o[3] for o in outs]), {k_: torch.stack([o[4][k_] for o in outs]) for k_ in keys})
+        self._require_local_state()
+        base, tg, dev = self._base, self.traj_gen, self.device
+        local = tg._prepare_local(a.to(dev, torch.float32).reshape(B * n_plans, P)).reshape(B, n_plans, P).contiguous()
+        tg.params = local[:, -1]
+        sched = self.plan_schedule(n_plans)
+        h, row0 = self._plans_handle(sched)
+        n_obs = len(self._obs_index_np)
+        from ..dist import result_block_bytes, result_block_flag_bytes, result_block_views
+        cache = self.__dict__.setdefault("_plan_out", {})
+        sets = cache.get(n_plans)
+        if sets is None:
+            sets = [dict(blocks=torch.zeros(n_plans, result_block_bytes(B), dtype=torch.uint8, device=dev),
+                         ret=torch.zeros(n_plans, B, dtype=torch.float64, device=dev),
+                         len=torch.zeros(n_plans, B, dtype=torch.int32, device=dev),
+                         flags=torch.zeros(n_plans, B, dtype=torch.uint8, device=dev),
+                         fb=torch.zeros(n_plans, 4, B, dtype=torch.bool, device=dev),
+                         info=torch.zeros(n_plans, B, 4, dtype=torch.float64, device=dev),
+                         obs=torch.zeros(n_plans, B, n_obs, dtype=torch.float32, device=dev)) for _ in range(2)]
+            cache[n_plans] = sets
+        o = sets[0]
+        sets.reverse()                # what this call returns stays valid during the next one
+        io = _lib.FgRolloutIO()
+        io.struct_size = C.sizeof(_lib.FgRolloutIO)
+        io.params = local.data_ptr()
+        io.ctx = base.ctx.data_ptr()
+        io.q, io.v, io.steps, io.done = base.q.data_ptr(), base.v.data_ptr(), base.steps.data_ptr(), base.done.data_ptr()
+        io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
+        io.use_cond = int(self.condition_set)
+        last_break = sched[-1][1] < int(round(self.duration / self.dt)) and sched[-1][0] + sched[-1][1] < int(self.env.spec.max_episode_steps)
+        io.write_cond = (2 if last_break else 1) if self.condition_on_desired else 0
+        io.ret, io.length, io.flags = o["ret"].data_ptr(), o["len"].data_ptr(), o["flags"].data_ptr()
+        io.obs, io.info, io.flag_bytes = o["obs"].data_ptr(), o["info"].data_ptr(), o["fb"].data_ptr()
+        io.prev_obs, io.prev_info = self._obs.data_ptr(), self._info.data_ptr()
+        io.n_plans, io.plan_T = n_plans, int(round(self.duration / self.dt))
+        for j, (s0, seg) in enumerate(sched):
+            io.plan_seg[j], io.plan_row0[j] = seg, row0[j]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(sched[0][1]), C.c_void_p(stream)))
+        self.plan_steps += n_plans
+        self.current_traj_steps += sum(seg for _, seg in sched)
+        if self.condition_on_desired and (n_plans > 1 or last_break):
+            self.condition_set = True
+        self._obs, self._info = o["obs"][-1], o["info"][-1]          # what a following step() carries over for frozen envs
+        length, ret = o["len"], o["ret"]
+        if self.reward_aggregation is np.mean:
+            ret = ret / length.clamp(min=1)
+        fb = o["fb"]
+        infos: Dict[str, Any] = {}
+        if base.env_kind in (_lib.ENV_HOLE_REACHER, _lib.ENV_VIAPOINT_REACHER):
+            infos["is_success"], infos["is_collided"] = fb[:, 2], fb[:, 3]
+            infos["end_effector"] = o["info"][:, :, 0:2]
+        elif base.env_kind == _lib.ENV_SIMPLE_REACHER:
+            infos["reward_dist"], infos["reward_ctrl"] = o["info"][:, :, 0], o["info"][:, :, 1]
+        infos["trajectory_length"] = length
+        return o["obs"], ret, fb[:, 0], fb[:, 1], infos
 
     def _planned_trajectory(self, local_params, out=None):
         tg = self.traj_gen
@@ -471,6 +752,9 @@ class BlackBoxWrapper(Wrapper):
             raise NotImplementedError("partial resets are not defined while envs share one replanning clock")
         if mask is None:
             mask = self._base.done
+        # a new episode: the phase generator un-finalizes like in reset() (black_box_wrapper.py:226), otherwise a learned tau /
+        # delay would stay frozen at the first episode's values
+        self.traj_gen.reset()
         obs = self._obs.clone()
         self._base.device_reset(None, obs_index=self._obs_index_np, time_aware=self._time_aware(), out=obs, mask=mask)
         return obs

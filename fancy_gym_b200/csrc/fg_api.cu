@@ -173,7 +173,7 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
     return fail(FG_ERR_INVALID, "fg_rollout: seg_steps %d outside 1..%d", seg_steps, h->cfg.n_steps);
   if (io->n_plans > 1) {       // plans looped inside the launch: the handle's tables hold every plan's rows
     if (io->n_plans > FG_MAX_PLANS) return fail(FG_ERR_INVALID, "fg_rollout: n_plans %d > FG_MAX_PLANS", io->n_plans);
-    if (h->cfg.mp_kind == FG_MP_TRAJ || io->seg_steps_env || io->dbg_actions || io->dbg_obs || io->dbg_rewards)
+    if (h->cfg.mp_kind == FG_MP_TRAJ || io->seg_steps_env || io->dbg_actions || io->dbg_obs || io->dbg_rewards || io->dbg_state)
       return fail(FG_ERR_UNSUPPORTED, "fg_rollout: n_plans > 1 needs a table-driven MP and no per-step / per-env-length buffers");
     if (io->plan_T < 2) return fail(FG_ERR_INVALID, "fg_rollout: plan_T %d < 2", io->plan_T);
     for (int j = 0; j < io->n_plans; ++j) {

@@ -840,6 +840,13 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
             for (int i = 0; i < N; ++i) io.dbg_actions[(b * c.T + t) * N + i] = a64[i];
           }
+          if (io.dbg_state) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              io.dbg_state[(b * c.T + t) * 2 * N + i] = q[i];
+              io.dbg_state[(b * c.T + t) * 2 * N + N + i] = VF ? (double)vf[i] : v[i];
+            }
+          }
           if (io.dbg_obs) {
             float so[FG_MAX_OBS];
             double ex, ey;

@@ -36,7 +36,7 @@ cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int
                       int max_smem_optin, const char** why) {
   // the per-step debug outputs of verbose >= 2 are a separate instantiation: the hot variant carries none of their code.
   // They always use run-time K (KC = 0) to keep the number of instantiations down.
-  if (io.dbg_actions || io.dbg_obs || io.dbg_rewards)
+  if (io.dbg_actions || io.dbg_obs || io.dbg_rewards || io.dbg_state)
     return launch_dbg<ENV, MP, MOTOR, N, 0, true>(c, io, B, seg_steps, stream, max_smem_optin, why);
   return launch_dbg<ENV, MP, MOTOR, N, KC, false>(c, io, B, seg_steps, stream, max_smem_optin, why);
 }

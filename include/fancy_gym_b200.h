@@ -175,6 +175,8 @@ typedef struct fg_rollout_io {
   int32_t plan_T;
   int32_t plan_seg[FG_MAX_PLANS];
   int32_t plan_row0[FG_MAX_PLANS];
+  double* dbg_state;       /* [B, T, 2 * dof] or NULL: joint angles and velocities after every executed step (current_pos /
+                              current_vel as black_box_wrapper.py:197 hands them to a state-dependent replanning_schedule) */
 } fg_rollout_io;
 
 /* Episode reset of the classic_control reachers on the device (replaces the host-side samplers

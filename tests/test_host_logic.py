@@ -272,3 +272,70 @@ def test_result_set_ring():
             seen.append(env._ret.data_ptr())
             assert env._result_block.data_ptr() == env._out_sets[env._out_i]["block"].data_ptr()
         assert len(set(seen)) == n and seen[:n] == seen[n:]
+
+
+# ---- re-planning schedules, plans laid out in advance, bounded handle cache, device median: host side ----------------
+def test_schedule_is_evaluated_once_and_plans_are_laid_out_like_the_reference_loop():
+    """black_box_wrapper.py:197: a plan breaks at the next step the schedule fires on while plan_steps < max_planning_times"""
+    calls = []
+
+    def sched(pos, vel, obs, action, t):
+        calls.append(t)
+        return t % 25 == 0
+
+    over = {"black_box_kwargs": {"replanning_schedule": sched, "max_planning_times": 4}}
+    env = fancy_gym.make("fancy_ProDMP/SimpleReacher-v0", num_envs=3, device="cpu", mp_config_override=over)
+    assert env._break_points() == [25, 50, 75, 100, 125, 150, 175, 200] and len(calls) == 200
+    env.traj_gen.set_duration(env.duration, env.dt)
+    for _ in range(5):
+        env._segment_steps(200)
+    assert len(calls) == 200                       # cached: no more host calls per step
+    assert env.plan_schedule(4) == [(0, 25), (25, 25), (50, 25), (75, 200)]      # the 4th plan is the last allowed: no break
+    env.current_traj_steps, env.plan_steps = 30, 1
+    assert env.plan_schedule(2) == [(30, 20), (50, 25)]
+    env.plan_steps = 0
+    env.current_traj_steps = 190
+    with pytest.raises(ValueError):
+        env.plan_schedule(3)                       # 190 -> 200, then the episode is over
+    free = fancy_gym.make("fancy_ProDMP/SimpleReacher-v0", num_envs=3, device="cpu",
+                          mp_config_override={"black_box_kwargs": {"replanning_schedule": lambda p, v, o, a, t: t % 60 == 0}})
+    assert free.plan_schedule(4) == [(0, 60), (60, 60), (120, 60), (180, 200)] and free._plans_fusable()
+
+
+def test_state_dependent_schedule_is_detected():
+    def sched(pos, vel, obs, action, t):
+        return float(np.abs(vel).max()) > 1.0
+
+    env = fancy_gym.make("fancy_ProDMP/SimpleReacher-v0", num_envs=1, device="cpu",
+                         mp_config_override={"black_box_kwargs": {"replanning_schedule": sched}})
+    assert env._break_points() is None and not env._plans_fusable()
+    env.traj_gen.set_duration(env.duration, env.dt)
+    with pytest.raises(NotImplementedError):
+        env._segment_steps(200)
+    env.schedule_host_callback = True
+    assert env._segment_steps(200) == (None, True)
+
+
+def test_handle_cache_is_bounded(monkeypatch):
+    """a learned scalar tau gives a new table key almost every episode: the cache evicts the least recently used handle"""
+    from fancy_gym_b200 import _lib
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=1, device="cpu",
+                         mp_config_override={"black_box_kwargs": {"max_cached_plans": 3}})
+    destroyed = []
+    monkeypatch.setattr(_lib.lib, "fg_destroy", lambda h: destroyed.append(h) or 0)
+    for i in range(5):
+        env._remember_handle(("k", i), f"h{i}")
+    assert list(env._handles) == [("k", 2), ("k", 3), ("k", 4)] and destroyed == ["h0", "h1"]
+    env._handles.clear()
+
+
+def test_masked_median_equals_numpy():
+    import torch
+    from fancy_gym_b200.black_box.black_box_wrapper import _masked_median
+    rng = np.random.default_rng(0)
+    r = rng.standard_normal((64, 50))
+    r[3, :4] = -np.inf
+    L = rng.integers(0, 51, size=64)
+    got = _masked_median(torch.as_tensor(r), torch.as_tensor(L)).numpy()
+    want = np.array([np.median(r[b, :L[b]]) if L[b] else 0.0 for b in range(64)])
+    assert np.array_equal(got, want)
