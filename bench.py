@@ -41,12 +41,17 @@ SIGMA = 0.25
 CPU_BATCH = 64                   # envs per oracle call in the CPU baseline (numpy-vectorised port)
 OPS_PER_ENV_STEP = 4356          # SURVEY.md §8d, HoleReacher/ProMP (FMA = 2, each collision test once per step)
 TRAJ_BYTES_PER_ENV = 2 * 200 * 5 * 4 + N_PARAMS * 4   # fg_trajgen: pos + vel out, params in
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at
-# the same sizes (profiles/r1_rollout_ncu_summary.txt, profiles/r1_trajgen_ncu_summary.txt)
-NCU_TRAFFIC_ROLLOUT = 14_299_648 + 0
-NCU_TRAFFIC_TRAJGEN = 26_288_384 + 2_039_226_000
-NCU_WARP_INSTRUCTIONS_ROLLOUT = 177_580_561     # smsp__inst_executed.sum of the same capture
-NCU_PIPES_ROLLOUT = dict(issue_active=70.8, alu=41.8, fma=32.3, xu=15.3, fp64=11.5)
+
+
+def ncu_numbers():
+    """dram bytes, executed warp instructions and pipe utilisations of the committed `ncu --set full` captures of the same
+    kernels at the same sizes: profiles/ncu_numbers.json, written by tools/ncu_to_json.py from profiles/*_ncu_summary.txt (a CPU
+    test keeps the two in step) — nothing ncu-derived is hard-coded here"""
+    p = os.path.join(ROOT, "profiles", "ncu_numbers.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return json.load(f)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -369,8 +374,10 @@ def main():
     fp32_peak = best
     steps_per_launch = env_steps / K
     achieved = OPS_PER_ENV_STEP * steps_per_launch / (kernel_ms * 1e-3) / 1e12
+    ncu = ncu_numbers()
+    ncu_roll, ncu_traj = ncu.get("rollout_config2", {}), ncu.get("trajgen_promp", {})
     roofline = dict(bound="fp32", achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak if fp32_peak else None,
-                    traffic=NCU_TRAFFIC_ROLLOUT if B == B_PER_GPU else None, traffic_unit="bytes per launch (ncu dram read + write)",
+                    traffic=ncu_roll.get("dram_bytes") if B == B_PER_GPU else None, traffic_unit="bytes per launch (ncu dram read + write)",
                     kernel="k_rollout<HOLE_REACHER, PROMP, vel, 5>", kernel_ms=kernel_ms,
                     peak_source="FFMA chain probe measured in this run (fg_ffma_probe); MEASURED_PEAKS.json has no CUDA-core figure",
                     note="achieved counts ALGORITHMIC ops: 4356 per env step incl. the literal 500 wall samples; the kernel uses an "
@@ -397,7 +404,7 @@ def main():
     traj_ms = sum(a.elapsed_time(b) for a, b in tev) / reps        # average launch duration over the timed launches
     traj_gbs = Bt * TRAJ_BYTES_PER_ENV / (traj_ms * 1e-3) / 1e9
     roofline_traj = dict(bound="hbm", achieved=traj_gbs, peak=hbm_peak, unit="GB/s", frac=traj_gbs / hbm_peak,
-                         traffic=NCU_TRAFFIC_TRAJGEN, traffic_unit="bytes per launch (ncu dram read + write; algorithmic: %d)" % (Bt * TRAJ_BYTES_PER_ENV),
+                         traffic=ncu_traj.get("dram_bytes"), traffic_unit="bytes per launch (ncu dram read + write; algorithmic: %d)" % (Bt * TRAJ_BYTES_PER_ENV),
                          kernel="k_trajgen_closed<PROMP,5,5>", kernel_ms=traj_ms, peak_source=hbm_src,
                          trajectories_per_s=Bt / (traj_ms * 1e-3), workload=f"{Bt} ProMP trajectories [200,5] pos+vel (2.1 GB output, > L2)")
 
@@ -498,6 +505,145 @@ def main():
     except Exception as e:      # noqa: BLE001  (an extra; never fails the bench)
         e2e_graph = dict(error=repr(e))
 
+    # ---------------- the other BASELINE.json configurations + a sustained run (extras; the headline stays configs[1]) ------
+    def make_sets(e, Bc, P, sigma, n_sets_c, seed0):
+        e_base = e.unwrapped
+        out = []
+        for i in range(n_sets_c):
+            e.reset(seed=seed0 + i)
+            out.append(dict(params=(sigma * torch.randn(Bc, P, generator=gen, device=dev)).contiguous(),
+                            state=SimpleNamespace(q=e_base.q.clone(), v=torch.zeros_like(e_base.v), steps=torch.zeros_like(e_base.steps),
+                                                  done=torch.zeros_like(e_base.done), ctx=e_base.ctx.clone())))
+        return out
+
+    def timed_launches(e, sets_c, reps, n_streams=1, min_seconds=0.0, gather=False):
+        """device-timed launches of the fused rollout from rotating input sets (keep_state: the launch itself is the step);
+        n_streams = 2 keeps two batches in flight (the wrapper's two result sets make that safe); returns ms per launch and
+        env steps per launch"""
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else [main]
+        tot = torch.zeros((), dtype=torch.int64, device=dev)
+        parts = [torch.zeros((), dtype=torch.int64, device=dev) for _ in streams]
+
+        def run(n):
+            for i in range(n):
+                st = streams[i % len(streams)]
+                with torch.cuda.stream(st):
+                    sc = sets_c[i % len(sets_c)]
+                    e.launch(sc["params"], state=sc["state"], keep_state=True)
+                    if gather:
+                        gather_results()
+                    parts[i % len(streams)] += e._len.sum()
+        run(3)
+        finish_gathers() if gather else None
+        sync_all()
+        for p_ in parts:
+            p_.zero_()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done_reps = 0
+        t_host = time.perf_counter()
+        a_.record(main)
+        for st in streams:
+            st.wait_stream(main)
+        while True:
+            run(reps)
+            done_reps += reps
+            if time.perf_counter() - t_host >= min_seconds:
+                break
+        if gather:
+            finish_gathers()
+        for st in streams:
+            main.wait_stream(st)
+        b_.record(main)
+        sync_all()
+        for p_ in parts:
+            tot += p_
+        ms = a_.elapsed_time(b_) / done_reps
+        return ms, int(tot.item()) / done_reps, done_reps
+
+    def agg(ms, steps_per_launch, Bc):
+        t_ = torch.tensor([ms], dtype=torch.float64, device=dev)
+        n_ = torch.tensor([steps_per_launch], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_, op=dist.ReduceOp.SUM)
+        ms_, st_ = float(t_.item()), float(n_.item())
+        return dict(ms_per_launch=ms_, env_steps_per_s=st_ / (ms_ * 1e-3), episodes_per_s=world * Bc / (ms_ * 1e-3),
+                    mean_episode_length=st_ / (world * Bc), envs_per_gpu=Bc)
+
+    extras = {}
+    try:
+        if world == 1:
+            # sustained: the headline launch repeated for >= 2 s with clocks and power sampled under load
+            with ClockSampler(local_rank) as cs:
+                ms, spl, n_done = timed_launches(env, sets, 200, min_seconds=2.0)
+            extras["sustained"] = dict(agg(ms, spl, B), launches=n_done, seconds=ms * n_done * 1e-3, clocks=cs.summary(),
+                                       workload="BASELINE configs[1], the timed launch of `value` repeated for >= 2 s")
+            # sigma = 1.0: most episodes end in a collision at different steps (re-packing of live envs inside the kernel)
+            s1 = make_sets(env, B, N_PARAMS, 1.0, 6, 50_000)
+            ms, spl, _ = timed_launches(env, s1, 40)
+            extras["sigma1"] = dict(agg(ms, spl, B), workload=f"{ENV_ID} x {B}, sigma = 1.0, one launch at a time")
+            ms, spl, _ = timed_launches(env, s1, 40, n_streams=2)
+            extras["sigma1"]["two_batches_in_flight"] = agg(ms, spl, B)
+            del s1
+            # config 3: fancy_DMP/ViaPointReacher-v0 x 262 144
+            e3 = fancy_gym.make("fancy_DMP/ViaPointReacher-v0", num_envs=1 << 18, device=dev, context_sampler="device")
+            s3 = make_sets(e3, 1 << 18, 30, 1.0, 3, 60_000)
+            ms, spl, _ = timed_launches(e3, s3, 10)
+            extras["config3"] = dict(agg(ms, spl, 1 << 18), workload="fancy_DMP/ViaPointReacher-v0 x 262144, weights N(0,1) (x50 inside)")
+            del e3, s3
+            # config 4: fancy_ProDMP/SimpleReacher-v0 x 65 536 with replanning t % 25, 4 plans, condition_on_desired:
+            # reset + ALL FOUR plans in one launch (step_plans), and the same with one launch per plan
+            over4 = {"black_box_kwargs": {"replanning_schedule": lambda p_, v_, o_, a_, t_: t_ % 25 == 0, "max_planning_times": 4,
+                                          "condition_on_desired": True}}
+            e4 = fancy_gym.make("fancy_ProDMP/SimpleReacher-v0", num_envs=B, device=dev, mp_config_override=over4)
+            acts = [torch.randn(B, 4, 12, generator=gen, device=dev) for _ in range(4)]
+
+            def episode4(i, fused):
+                e4.reset(seed=None)
+                if fused:
+                    return e4.step_plans(acts[i % 4])[4]["trajectory_length"].sum()
+                tot4 = 0
+                for j in range(4):
+                    tot4 = tot4 + e4.step(acts[i % 4][:, j])[4]["trajectory_length"].sum()
+                return tot4
+            c4 = {}
+            for fused in (True, False):
+                e4.reset(seed=1)
+                for i in range(3):
+                    episode4(i, fused)
+                torch.cuda.synchronize(dev)
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                tot4 = 0
+                for i in range(20):
+                    tot4 = tot4 + episode4(i, fused)
+                b_.record()
+                torch.cuda.synchronize(dev)
+                c4["one_launch" if fused else "launch_per_plan"] = agg(a_.elapsed_time(b_) / 20, int(tot4) / 20, B)
+            extras["config4"] = dict(c4["one_launch"], launch_per_plan=c4["launch_per_plan"],
+                                     workload="fancy_ProDMP/SimpleReacher-v0 x 65536, replanning t % 25, 4 plans, condition_on_desired; "
+                                              "per episode batch: reset + step_plans (one fused launch for all four plans)")
+            del e4, acts
+        # config 5: 2^20 envs per GPU (N > 1: with the per-step all-gather of every rank's results)
+        B5 = 1 << 20
+        e5 = fancy_gym.make(ENV_ID, num_envs=B5, device=dev, context_sampler="device", mp_config_override={"black_box_kwargs": {"result_sets": RING}})
+        s5 = make_sets(e5, B5, N_PARAMS, args.sigma, 2, 70_000 + 10 * rank)
+        if world > 1:
+            env_small = env
+            env = e5                    # gather_results() exchanges env._result_block
+            gathered = [torch.zeros(world * e5._result_block.numel(), dtype=torch.uint8, device=dev) for _ in range(RING)]
+        ms, spl, _ = timed_launches(e5, s5, 6, gather=world > 1)
+        extras["config5" if world > 1 else "config5_1gpu"] = dict(
+            agg(ms, spl, B5), workload=f"{ENV_ID} x {B5} envs per GPU, sigma = {args.sigma}" +
+            (", all_gather(return, length, flags) of every rank per launch" if world > 1 else ""))
+        if world > 1:
+            env = env_small
+        del e5, s5
+    except Exception as ex:      # noqa: BLE001  (extras never fail the bench line)
+        extras["error"] = repr(ex)
+    torch.cuda.empty_cache()
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -506,13 +652,14 @@ def main():
         ref.close()
 
     clocks = clk.summary()
-    if B == B_PER_GPU and clocks.get("sm_mhz"):
+    if B == B_PER_GPU and clocks.get("sm_mhz") and ncu_roll.get("warp_instructions"):
         # what the machine actually executed: warp instructions of the committed ncu capture of this launch / live kernel time
         # against the issue rate (4 schedulers x 1 instruction per clock per SM at the sampled SM clock); pipe shares: the capture's
-        roofline["executed"] = dict(warp_instructions_per_launch=NCU_WARP_INSTRUCTIONS_ROLLOUT,
-                                    issue_slot_frac=NCU_WARP_INSTRUCTIONS_ROLLOUT / (kernel_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sm_count * 4),
-                                    ncu_pct_of_peak_sustained_active=NCU_PIPES_ROLLOUT,
-                                    source="profiles/r1_rollout_ncu_summary.txt (ncu --set full of this launch)")
+        roofline["executed"] = dict(warp_instructions_per_launch=ncu_roll["warp_instructions"],
+                                    thread_instructions_per_env_step=ncu_roll["warp_instructions"] * ncu_roll.get("threads_per_instruction", 32.0) / steps_per_launch,
+                                    issue_slot_frac=ncu_roll["warp_instructions"] / (kernel_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * sm_count * 4),
+                                    ncu_pct_of_peak_sustained_active=ncu_roll.get("pipes"),
+                                    source=ncu_roll.get("source"))
     if rank == 0:
         line = dict(metric="env-steps/sec (fancy_ProMP/HoleReacher-v0 MP black-box rollout)", value=value, unit="env-steps/s",
                     n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms_max / K, higher_is_better=True, scaling="weak",
@@ -524,7 +671,7 @@ def main():
                                 collective="all_gather(return,length,flags) per step, asynchronous behind the next rollouts (ring of %d result sets)" % RING if world > 1 else "none"),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_sync=e2e_sync, e2e_graph=e2e_graph,
-                    clocks=clocks, gpu_launches=K)
+                    clocks=clocks, gpu_launches=K, configs=extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -30,3 +30,18 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_ncu_numbers_json_is_what_the_committed_summaries_say():
+    """bench.py takes every ncu-derived number (dram bytes, executed instructions, pipe shares) from profiles/ncu_numbers.json;
+    that file must be exactly what tools/ncu_to_json.py derives from the committed profiles/*_ncu_summary.txt, and bench.py
+    itself must not carry such literals"""
+    sys.path.insert(0, ROOT)
+    from tools import ncu_to_json
+    with open(os.path.join(ROOT, "profiles", "ncu_numbers.json")) as f:
+        stored = json.load(f)
+    assert stored == json.loads(json.dumps(ncu_to_json.build()))
+    assert "rollout_config2" in stored and stored["rollout_config2"]["warp_instructions"] > 0
+    assert stored["rollout_config2"]["dram_bytes"] > 0 and stored["trajgen_promp"]["dram_bytes"] > 0
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "NCU_TRAFFIC" not in src and "NCU_WARP_INSTRUCTIONS" not in src and "NCU_PIPES" not in src
