@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -37,14 +38,21 @@ struct fg_handle {
   float* d_tab_a;
   float* d_tab_b;
   float* d_quad_rec;
+  // work queues of persistent rollout grids: kQueues pairs of device words (next env, finished blocks), zero between
+  // launches (the kernel resets its pair); concurrent launches on different streams take different pairs
+  unsigned* d_queue;
+  mutable std::atomic<unsigned> next_queue;
   int max_smem_optin;
   int sm_count;
 };
+static constexpr unsigned kQueues = 64;
 
 extern "C" {
 
 const char* fg_last_error(void) { return g_err; }
 int32_t fg_abi_version(void) { return FG_ABI_VERSION; }
+
+fg_status fg_destroy(fg_handle* h);
 
 fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
   if (!cfg || !out) return fail(FG_ERR_INVALID, "fg_create: null argument");
@@ -66,11 +74,23 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->d_tab_a = h->d_tab_b = h->d_quad_rec = nullptr;
+  h->d_queue = nullptr;
+  h->next_queue = 0;
+  // (any failure from here on frees what has been allocated and restores the caller's current device)
+#define FG_CUDA_H(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      cudaSetDevice(prev);                                                                \
+      fg_destroy(h);                                                                      \
+      return fail(FG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                  \
+    }                                                                                     \
+  } while (0)
   int prev = 0;
-  FG_CUDA(cudaGetDevice(&prev));
-  FG_CUDA(cudaSetDevice(device));
-  FG_CUDA(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  FG_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  FG_CUDA_H(cudaGetDevice(&prev));
+  FG_CUDA_H(cudaSetDevice(device));
+  FG_CUDA_H(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  FG_CUDA_H(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
 
   fg::DevCfg& d = h->dev;
   memset(&d, 0, sizeof(d));
@@ -93,7 +113,8 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
   if (cfg->env_kind == FG_ENV_TOY) d.n_obs_full = 1 + (cfg->time_aware ? 1 : 0);
   for (int j = 0; j < cfg->n_obs_out; ++j) {
     if (cfg->obs_index[j] < 0 || cfg->obs_index[j] >= d.n_obs_full) {
-      delete h;
+      cudaSetDevice(prev);
+      fg_destroy(h);
       return fail(FG_ERR_INVALID, "obs_index[%d]=%d outside the %d-wide step observation", j, cfg->obs_index[j], d.n_obs_full);
     }
     d.obs_index[j] = cfg->obs_index[j];
@@ -107,10 +128,10 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
   }
   na = (size_t)T * d.cols_a; nb = (size_t)d.rows_b * d.cols_b;
   if (na) {
-    FG_CUDA(cudaMalloc(&h->d_tab_a, na * sizeof(float)));
-    FG_CUDA(cudaMemcpy(h->d_tab_a, cfg->tab_a, na * sizeof(float), cudaMemcpyHostToDevice));
-    FG_CUDA(cudaMalloc(&h->d_tab_b, nb * sizeof(float)));
-    FG_CUDA(cudaMemcpy(h->d_tab_b, cfg->tab_b, nb * sizeof(float), cudaMemcpyHostToDevice));
+    FG_CUDA_H(cudaMalloc(&h->d_tab_a, na * sizeof(float)));
+    FG_CUDA_H(cudaMemcpy(h->d_tab_a, cfg->tab_a, na * sizeof(float), cudaMemcpyHostToDevice));
+    FG_CUDA_H(cudaMalloc(&h->d_tab_b, nb * sizeof(float)));
+    FG_CUDA_H(cudaMemcpy(h->d_tab_b, cfg->tab_b, nb * sizeof(float), cudaMemcpyHostToDevice));
   }
   d.tab_a = h->d_tab_a; d.tab_b = h->d_tab_b;
   if (cfg->mp_kind == FG_MP_PROMP || cfg->mp_kind == FG_MP_PRODMP) {
@@ -136,15 +157,18 @@ fg_status fg_create(const fg_config* cfg, int32_t device, fg_handle** out) {
         }
       }
     }
-    FG_CUDA(cudaMalloc(&h->d_quad_rec, rec.size() * sizeof(float)));
-    FG_CUDA(cudaMemcpy(h->d_quad_rec, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FG_CUDA_H(cudaMalloc(&h->d_quad_rec, rec.size() * sizeof(float)));
+    FG_CUDA_H(cudaMemcpy(h->d_quad_rec, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice));
     d.quad_rec = reinterpret_cast<const float4*>(h->d_quad_rec);
     d.quad_rec4 = rec4;
   }
+  FG_CUDA_H(cudaMalloc(&h->d_queue, 2 * kQueues * sizeof(unsigned)));
+  FG_CUDA_H(cudaMemset(h->d_queue, 0, 2 * kQueues * sizeof(unsigned)));
   h->cfg.tab_a = h->cfg.tab_b = nullptr;   // host pointers are not retained
-  FG_CUDA(cudaSetDevice(prev));
+  FG_CUDA_H(cudaSetDevice(prev));
   *out = h;
   return FG_OK;
+#undef FG_CUDA_H
 }
 
 fg_status fg_destroy(fg_handle* h) {
@@ -152,6 +176,7 @@ fg_status fg_destroy(fg_handle* h) {
   if (h->d_tab_a) cudaFree(h->d_tab_a);
   if (h->d_tab_b) cudaFree(h->d_tab_b);
   if (h->d_quad_rec) cudaFree(h->d_quad_rec);
+  if (h->d_queue) cudaFree(h->d_queue);
   delete h;
   return FG_OK;
 }
@@ -196,8 +221,9 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
   FG_CUDA(cudaGetDevice(&prev));
   if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));
   const char* why = nullptr;
+  unsigned* queue = h->d_queue + 2 * (h->next_queue.fetch_add(1u) % kQueues);
   cudaError_t e = fg::launch_rollout(h->dev, h->cfg.env_kind, h->cfg.mp_kind, *io, B, seg_steps,
-                                     (cudaStream_t)stream, h->max_smem_optin, &why);
+                                     (cudaStream_t)stream, h->max_smem_optin, &why, queue, h->sm_count);
   if (prev != h->device) cudaSetDevice(prev);
   if (why) return fail(FG_ERR_UNSUPPORTED, "fg_rollout: %s", why);
   if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_rollout launch: %s", cudaGetErrorString(e));

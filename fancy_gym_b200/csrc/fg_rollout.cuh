@@ -89,7 +89,7 @@ __host__ __device__ inline size_t rollout_smem_bytes(int T, int cols_a, int rows
 template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
 __global__ void __launch_bounds__(kRolloutThreads, FG_ROLLOUT_MINB)
 k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
-          const int seg_steps) {
+          const int seg_steps, unsigned* __restrict__ queue) {
   using SL = SlotLayout<ENV, MP, MOTOR, N, KC>;
   constexpr bool VF = SL::VF, VEL_ONLY = SL::VEL_ONLY;
   extern __shared__ __align__(16) float smem[];
@@ -150,6 +150,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     ctl[0] = 0;
     ctl[1] = 0;
     ctl[2] = 0;
+    ctl[3] = 0;        // work queue exhausted
   }
   __syncthreads();
 
@@ -368,7 +369,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       s[(SL::W_INFO + 2) * BD] = (unsigned)__double2loint(info1); s[(SL::W_INFO + 3) * BD] = (unsigned)__double2hiint(info1);
     }
     unsigned* z = s + SL::W_SCAL * BD;
-    z[SL::S_B * BD] = (unsigned)(b - b0);
+    z[SL::S_B * BD] = (unsigned)b;
     z[SL::S_STEPS * BD] = (unsigned)steps;
     z[SL::S_K * BD] = (unsigned)k;
     z[SL::S_TR * BD] = (unsigned)tr;
@@ -404,7 +405,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       info1 = __hiloint2double((int)s[(SL::W_INFO + 3) * BD], (int)s[(SL::W_INFO + 2) * BD]);
     }
     const unsigned* z = s + SL::W_SCAL * BD;
-    b = b0 + (long long)z[SL::S_B * BD];
+    b = (long long)z[SL::S_B * BD];
     steps = (int)z[SL::S_STEPS * BD];
     k = (int)z[SL::S_K * BD];
     tr = (int)z[SL::S_TR * BD];
@@ -490,71 +491,76 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     ret = r_keep;
   };
 
+  // ---- start env `b` in slot `own` (its parameters of the first plan are in wsm already): true if it runs ----
+  auto start_env = [&]() -> bool {
+    if (io.done[b]) {   // episode already over: frozen (oracle/blackbox.py keeps such envs untouched)
+      for (int kk = 0; kk < n_plans; ++kk) {
+        const long long o = (long long)kk * B + b;
+        io.ret[o] = 0.0;
+        io.length[o] = 0;
+        io.flags[o] = 0;
+        if (io.flag_bytes)
+          for (int i = 0; i < 4; ++i) io.flag_bytes[((long long)kk * 4 + i) * B + b] = 0;
+        if (io.prev_obs)
+          for (int j = 0; j < c.n_obs_out; ++j) io.obs[o * c.n_obs_out + j] = io.prev_obs[b * c.n_obs_out + j];
+        if (io.prev_info)
+          for (int j = 0; j < 4; ++j) io.info[o * 4 + j] = io.prev_info[b * 4 + j];
+      }
+      fl = kSlotEmpty;
+      return false;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if constexpr (ENV == FG_ENV_TOY) {   // ToyWrapper: current_pos = 1, current_vel = 0 (test_black_box.py:48-56)
+        q[i] = 1.0;
+        v[i] = 0.0;
+        vf[i] = 0.f;
+      } else {
+        q[i] = io.q[b * N + i];
+        v[i] = io.v[b * N + i];
+        vf[i] = (float)v[i];
+      }
+    }
+    steps = io.steps[b];
+    k = 0;
+    ret = 0.0;
+    load_context();
+    if constexpr (ENV == FG_ENV_HOLE_REACHER) {
+      if (c.rew_fct == 2 && steps > 0) latch_put(io.info[b * 4 + 2], io.info[b * 4 + 3]);   // a later plan segment of the episode
+      else latch_put(0.0, 0.0);
+    }
+    float ybc[N], vbc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (io.use_cond) {
+        ybc[i] = io.cond_pos[b * N + i];
+        vbc[i] = io.cond_vel[b * N + i];
+      } else {
+        ybc[i] = (float)q[i];
+        vbc[i] = VF ? vf[i] : (float)v[i];
+      }
+    }
+    tr = io.n_plans > 1 ? io.plan_row0[0] : 0;
+    tr_end = tr + plan_seg(0);
+    tr_last = tr + io.plan_T - 1;
+    plan_setup(ybc, vbc);
+    fl = kSlotLive;
+    if (tr_end <= tr) fl = kSlotPending;  // nothing to execute: reports 0 steps
+    return fl == kSlotLive;
+  };
+
   // =================================================================================================================
   // initial binding: thread tid <-> slot tid <-> env b0 + tid
   // =================================================================================================================
   {
-    const bool valid = b < B;
     bool live = false;
-    if (valid) {
-      if (io.done[b]) {   // episode already over: frozen (oracle/blackbox.py keeps such envs untouched)
-        for (int kk = 0; kk < n_plans; ++kk) {
-          const long long o = (long long)kk * B + b;
-          io.ret[o] = 0.0;
-          io.length[o] = 0;
-          io.flags[o] = 0;
-          if (io.flag_bytes)
-            for (int i = 0; i < 4; ++i) io.flag_bytes[((long long)kk * 4 + i) * B + b] = 0;
-          if (io.prev_obs)
-            for (int j = 0; j < c.n_obs_out; ++j) io.obs[o * c.n_obs_out + j] = io.prev_obs[b * c.n_obs_out + j];
-          if (io.prev_info)
-            for (int j = 0; j < 4; ++j) io.info[o * 4 + j] = io.prev_info[b * 4 + j];
-        }
-      } else {
-        live = true;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          if constexpr (ENV == FG_ENV_TOY) {   // ToyWrapper: current_pos = 1, current_vel = 0 (test_black_box.py:48-56)
-            q[i] = 1.0;
-            v[i] = 0.0;
-            vf[i] = 0.f;
-          } else {
-            q[i] = io.q[b * N + i];
-            v[i] = io.v[b * N + i];
-            vf[i] = (float)v[i];
-          }
-        }
-        steps = io.steps[b];
-        load_context();
-        if constexpr (ENV == FG_ENV_HOLE_REACHER) {
-          if (c.rew_fct == 2 && steps > 0) latch_put(io.info[b * 4 + 2], io.info[b * 4 + 3]);   // a later plan segment of the episode
-          else latch_put(0.0, 0.0);
-        }
-        float ybc[N], vbc[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          if (io.use_cond) {
-            ybc[i] = io.cond_pos[b * N + i];
-            vbc[i] = io.cond_vel[b * N + i];
-          } else {
-            ybc[i] = (float)q[i];
-            vbc[i] = VF ? vf[i] : (float)v[i];
-          }
-        }
-        tr = io.n_plans > 1 ? io.plan_row0[0] : 0;
-        tr_end = tr + plan_seg(0);
-        tr_last = tr + io.plan_T - 1;
-        plan_setup(ybc, vbc);
-        fl = kSlotLive;
-        if (tr_end <= tr) fl = kSlotPending;  // nothing to execute: reports 0 steps
-      }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, live && fl == kSlotLive);
+    if (b < B) live = start_env();
+    const unsigned m = __ballot_sync(0xffffffffu, live);
     if (lane == 0 && m) {
       atomicAdd(const_cast<int*>(&ctl[1]), __popc(m));
       atomicAdd(const_cast<int*>(&ctl[2]), 1);       // warps that run something
     }
-    if (!live) sst[(SL::W_SCAL + SL::S_FLAGS) * BD + tid] = kSlotEmpty;
+    if (fl == kSlotEmpty) sst[(SL::W_SCAL + SL::S_FLAGS) * BD + tid] = kSlotEmpty;
   }
   __syncthreads();
   // (envs that were already done / a ragged last block: re-pack right away when that frees a warp)
@@ -934,25 +940,67 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     const unsigned lt = (1u << lane) - 1u;
     if (st == kSlotLive) live_list[lbase + __popc(lm & lt)] = (unsigned short)tid;
     if (st == kSlotPending) pend_list[pbase + __popc(pm & lt)] = (unsigned short)tid;
+    // Stopped envs are finished 32 at a time by the threads from the top of the block (warps that have nothing to run),
+    // or all of them once nothing is running any more.  With a work queue (more envs than resident threads) every thread
+    // that finishes an env starts the next env of the queue in the same slot: the block stays full until the queue is empty.
+    const bool do_finish = n_pend > 0 && (n_pend >= 32 || n_live == 0);
+    const int n_fin = do_finish ? n_pend : 0;
     if (tid == 0) {
+      unsigned base = 0xffffffffu;
+      if (queue && n_fin > 0 && ctl[3] == 0) {
+        base = atomicAdd(queue, (unsigned)n_fin);
+        if ((long long)base + (long long)gridDim.x * BD >= B) ctl[3] = 1;       // the queue has run dry
+      }
+      ctl[4] = (int)base;
       ctl[0] = 0;
-      ctl[1] = n_live;
-      ctl[2] = (n_live + 31) >> 5;
+      ctl[1] = n_live;          // (+ the envs started from the queue: added by their threads below)
+      ctl[2] = 0;               // warps that run something: counted below
     }
     __syncthreads();                      // the lists are complete
-    // Stopped envs are finished 32 at a time by the threads from the top of the block (warps that have nothing to run),
-    // or all of them once nothing is running any more
-    const bool do_finish = n_pend > 0 && (n_pend >= 32 || n_live == 0);
     have = bound = false;
     if (tid < n_live) {
       pick_up(live_list[tid]);
       have = bound = true;
-    } else if (do_finish && BD - 1 - tid < n_pend) {
-      pick_up(pend_list[BD - 1 - tid]);
+    } else if (BD - 1 - tid < n_fin) {
+      const int j = BD - 1 - tid;
+      pick_up(pend_list[j]);
       finish();
-      sst[(SL::W_SCAL + SL::S_FLAGS) * BD + own] = kSlotEmpty;
+      fl = kSlotEmpty;
+      const unsigned base = (unsigned)ctl[4];
+      const long long nb = (long long)gridDim.x * BD + (long long)base + j;
+      if (queue && base != 0xffffffffu && nb < B) {        // the next env of the queue, in the slot that has just become free
+        b = nb;
+        if constexpr (HAS_W) {
+          const float* pk = io.params + b * PS;
+          for (int idx = 0; idx < P; ++idx) put_param(own, idx, pk[idx]);
+        }
+        if (start_env()) {
+          have = true;
+          atomicAdd(const_cast<int*>(&ctl[1]), 1);
+        }
+        bound = fl != kSlotEmpty;
+      }
+      if (!bound) sst[(SL::W_SCAL + SL::S_FLAGS) * BD + own] = kSlotEmpty;
     }
-    if (n_live == 0) break;               // (then every stopped env has just been finished)
+    if (__any_sync(0xffffffffu, have) && lane == 0) atomicAdd(const_cast<int*>(&ctl[2]), 1);
+    if (n_live == 0) {
+      if (!(queue && n_fin > 0)) break;   // every stopped env has just been finished and nothing was started
+      // nothing was running: did the queue hand out envs?  (only in this case does anybody wait for the finishing threads)
+      __syncthreads();
+      if (ctl[1] == 0) {
+        // no: the block ends, unless an env was started that has nothing to execute (it is pending: one more pass)
+        if (!__syncthreads_or(bound)) break;
+        if (tid == 0) ctl[0] = 1;
+        __syncthreads();
+      }
+    }
+  }
+  if (queue && tid == 0) {                // the last block of the launch resets the queue for the next launch
+    const unsigned done_blocks = atomicAdd(queue + 1, 1u);
+    if (done_blocks == gridDim.x - 1) {
+      queue[0] = 0u;
+      queue[1] = 0u;
+    }
   }
 #undef WSM
 }

@@ -7,7 +7,7 @@ namespace fg {
 
 template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
 cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                      int max_smem_optin, const char** why) {
+                      int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
   const int pw = N * weight_slots(MP, c.K);
   const size_t smem = rollout_smem_bytes(c.T, c.cols_a, c.rows_b, c.cols_b, pw, SlotLayout<ENV, MP, MOTOR, N, KC>::WORDS,
                                          kRolloutThreads);
@@ -20,48 +20,65 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const long long blocks = (B + kRolloutThreads - 1) / kRolloutThreads;
+  long long blocks = (B + kRolloutThreads - 1) / kRolloutThreads;
   fg_rollout_io iok = io;
   if (iok.n_plans <= 1) {      // one plan: the whole table is that plan
     iok.n_plans = 1;
     iok.plan_T = c.T;
     iok.plan_row0[0] = 0;
   }
-  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps);
+  // More envs than the GPU holds at once: a persistent grid (every SM full) whose threads take the next env from a work
+  // queue when the one they ran is finished, instead of blocks that drain while their last envs run out.
+  unsigned* q = nullptr;
+  if (queue) {
+    static thread_local size_t occ_smem = ~(size_t)0;
+    static thread_local int occ_blocks = 0;
+    if (occ_smem != smem) {
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, kern, kRolloutThreads, smem);
+      if (e != cudaSuccess) return e;
+      occ_smem = smem;
+    }
+    const long long resident = (long long)occ_blocks * sm_count;
+    if (resident > 0 && blocks > 2 * resident) {
+      blocks = resident;
+      q = queue;
+    }
+  }
+  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps, q);
   return cudaGetLastError();
 }
 
 template <int ENV, int MP, bool MOTOR, int N, int KC>
 cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                      int max_smem_optin, const char** why) {
+                      int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
   // the per-step debug outputs of verbose >= 2 are a separate instantiation: the hot variant carries none of their code.
   // They always use run-time K (KC = 0) to keep the number of instantiations down.
   if (io.dbg_actions || io.dbg_obs || io.dbg_rewards || io.dbg_state)
-    return launch_dbg<ENV, MP, MOTOR, N, 0, true>(c, io, B, seg_steps, stream, max_smem_optin, why);
-  return launch_dbg<ENV, MP, MOTOR, N, KC, false>(c, io, B, seg_steps, stream, max_smem_optin, why);
+    return launch_dbg<ENV, MP, MOTOR, N, 0, true>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+  return launch_dbg<ENV, MP, MOTOR, N, KC, false>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
 }
 
 template <int ENV, int MP, bool MOTOR, int N>
 cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                       int max_smem_optin, const char** why) {
+                       int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
   // num_basis = 5 is the registry default of every MP type (registry.py:76-125): register-resident weights
   // (instantiated for the registered link counts only — 5 links, SimpleReacher's 2 — to keep the library small)
   if constexpr (MP != FG_MP_TRAJ && (N == 5 || N == 2)) {
     // (without a motor law the KC instantiation assumes velocity control: position control takes the run-time-K variant)
     if (c.K == 5 && (MOTOR || c.ctrl == FG_CTRL_VELOCITY))
-      return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why);
+      return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
   }
-  return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why);
+  return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
 }
 
 template <int ENV, int N>
 cudaError_t launch_mp_ctrl(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,
-                           cudaStream_t stream, int max_smem_optin, const char** why) {
+                           cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
   const bool motor = c.ctrl == FG_CTRL_MOTOR;
 #define FG_CASE(MPK)                                                                                             \
   case MPK:                                                                                                      \
-    return motor ? launch_one<ENV, MPK, true, N>(c, io, B, seg_steps, stream, max_smem_optin, why)               \
-                 : launch_one<ENV, MPK, false, N>(c, io, B, seg_steps, stream, max_smem_optin, why);
+    return motor ? launch_one<ENV, MPK, true, N>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count)  \
+                 : launch_one<ENV, MPK, false, N>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
   switch (mp_kind) {
     FG_CASE(FG_MP_PROMP)
     FG_CASE(FG_MP_DMP)

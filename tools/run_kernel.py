@@ -44,6 +44,8 @@ def trajgen(env_id, phase=None, B=1 << 18):
 
 if what == "rollout_sigma1":
     rollout("fancy_ProMP/HoleReacher-v0", 65536, 1.0)
+elif what == "rollout_1m_sigma1":
+    rollout("fancy_ProMP/HoleReacher-v0", 1 << 20, 1.0)
 elif what == "rollout_1m":
     rollout("fancy_ProMP/HoleReacher-v0", 1 << 20, 0.25)
 elif what == "rollout_config3":
