@@ -285,17 +285,57 @@ def main():
                          state=SimpleNamespace(q=base.q.clone(), v=torch.zeros_like(base.v), steps=torch.zeros_like(base.steps),
                                                done=torch.zeros_like(base.done), ctx=base.ctx.clone())))
 
-    from fancy_gym_b200.dist import all_gather_result_blocks
+    from fancy_gym_b200.dist import PeerResultExchange, all_gather_result_blocks
     gathered = [torch.zeros(world * env._result_block.numel(), dtype=torch.uint8, device=dev) for _ in range(RING)] if world > 1 else None
     in_flight = []
     n_gathers = [0]
 
+    # Multi-GPU exchange.  Default: FUSED into the rollout — every env's result row is stored by the kernel itself into the
+    # gather buffer of every rank over NVLink peer memory (fg_rollout_io.peer_bufs, torch symmetric memory), the ranks only
+    # order a one-CTA barrier behind the launch on a side stream: no collective kernel shares the SMs with the rollout.
+    # FG_BENCH_EXCHANGE=nccl selects the overlapped ncclAllGather of round 1 (also the fallback if peer memory cannot be mapped).
+    exchange = {"mode": "none", "peer": None, "note": None}
+
+    def make_exchange(e):
+        if world == 1:
+            return None
+        ok, err, px = 1, None, None
+        if os.environ.get("FG_BENCH_EXCHANGE", "peer") == "peer":
+            try:
+                px = PeerResultExchange(e, ring=4)
+            except Exception as ex_:      # noqa: BLE001
+                ok, err = 0, repr(ex_)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if px is not None:
+                px.detach(e)
+            exchange["note"] = err
+            return None
+        return px
+
+    exchange["peer"] = make_exchange(env)
+    exchange["mode"] = "none" if world == 1 else ("peer-stores" if exchange["peer"] is not None else "nccl-allgather")
+
+    def pre_launch():
+        """peer stores: launch j overwrites the ring slot of launch j - ring; every rank has read it once the barrier of launch
+        j - ring + 1 has passed"""
+        px = exchange["peer"]
+        if px is not None:
+            while len(in_flight) > px.ring - 2:
+                in_flight.pop(0).wait()
+
     def gather_results():
-        """returns / lengths / flags of every rank to every rank: ONE NCCL all-gather of the step's result block per step,
+        """returns / lengths / flags of every rank to every rank.  peer-stores: already written by the rollout kernel; publish
+        = barrier on the side stream.  nccl-allgather: ONE NCCL all-gather of the step's result block per step,
         no packing kernels (fancy_gym_b200/dist).  The exchange of step k runs on NCCL's stream while the rollouts of the
         next steps (which write the OTHER result sets of the wrapper's ring) run on ours; before step k starts ITS
         exchange the stream waits for that of step k - (RING - 1), so no rollout overwrites a block that is still being sent."""
-        if world > 1:
+        if exchange["peer"] is not None:
+            in_flight.append(exchange["peer"].publish())
+        elif world > 1:
             while len(in_flight) > RING - 2:
                 in_flight.pop(0).wait()
             in_flight.append(all_gather_result_blocks(env._result_block, out=gathered[n_gathers[0] % RING], async_op=True)[1])
@@ -308,6 +348,7 @@ def main():
             in_flight.pop(0).wait()
 
     def step_device(s):
+        pre_launch()
         env.launch(s["params"], state=s["state"], keep_state=True)
         gather_results()
 
@@ -336,6 +377,7 @@ def main():
         host_t0 = time.perf_counter()
         for i in range(K):
             s = sets[(W + i) % n_sets]
+            pre_launch()
             kev[i][0].record()
             env.launch(s["params"], state=s["state"], keep_state=True)
             kev[i][1].record()
@@ -530,6 +572,8 @@ def main():
                 st = streams[i % len(streams)]
                 with torch.cuda.stream(st):
                     sc = sets_c[i % len(sets_c)]
+                    if gather:
+                        pre_launch()
                     e.launch(sc["params"], state=sc["state"], keep_state=True)
                     if gather:
                         gather_results()
@@ -630,15 +674,19 @@ def main():
         e5 = fancy_gym.make(ENV_ID, num_envs=B5, device=dev, context_sampler="device", mp_config_override={"black_box_kwargs": {"result_sets": RING}})
         s5 = make_sets(e5, B5, N_PARAMS, args.sigma, 2, 70_000 + 10 * rank)
         if world > 1:
-            env_small = env
+            env_small, peer_small = env, exchange["peer"]
             env = e5                    # gather_results() exchanges env._result_block
+            finish_gathers()
+            if peer_small is not None:
+                exchange["peer"] = make_exchange(e5)
             gathered = [torch.zeros(world * e5._result_block.numel(), dtype=torch.uint8, device=dev) for _ in range(RING)]
         ms, spl, _ = timed_launches(e5, s5, 6, gather=world > 1)
         extras["config5" if world > 1 else "config5_1gpu"] = dict(
             agg(ms, spl, B5), workload=f"{ENV_ID} x {B5} envs per GPU, sigma = {args.sigma}" +
             (", all_gather(return, length, flags) of every rank per launch" if world > 1 else ""))
         if world > 1:
-            env = env_small
+            finish_gathers()
+            env, exchange["peer"] = env_small, peer_small
         del e5, s5
     except Exception as ex:      # noqa: BLE001  (extras never fail the bench line)
         extras["error"] = repr(ex)
@@ -668,7 +716,12 @@ def main():
                                 envs_per_gpu=B, n_params=N_PARAMS, sigma=args.sigma, max_episode_steps=200,
                                 contexts="device sampler (numpy-exact PCG64 streams, fg_reset)", parallelism=f"env-shard x{world}",
                                 l2="inputs rotate over %d sets (%.0f MB > 126 MB L2)" % (n_sets, n_sets * set_bytes / 1e6),
-                                collective="all_gather(return,length,flags) per step, asynchronous behind the next rollouts (ring of %d result sets)" % RING if world > 1 else "none"),
+                                collective={"none": "none",
+                                            "peer-stores": "fused: the rollout kernel stores (return, length, flags) of every env into every rank's gather "
+                                                           "buffer over NVLink peer memory; one barrier per step on a side stream (ring of 4 slots)",
+                                            "nccl-allgather": "all_gather(return,length,flags) per step, asynchronous behind the next rollouts "
+                                                              "(ring of %d result sets)" % RING}[exchange["mode"]],
+                                exchange_note=exchange["note"]),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_sync=e2e_sync, e2e_graph=e2e_graph,
                     clocks=clocks, gpu_launches=K, configs=extras)

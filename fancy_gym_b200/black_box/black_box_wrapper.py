@@ -416,6 +416,9 @@ class BlackBoxWrapper(Wrapper):
                 io.dbg_obs = dbg["obs"].data_ptr()
             if "state" in dbg:
                 io.dbg_state = dbg["state"].data_ptr()
+        peer = getattr(self, "_peer_exchange", None)
+        if peer is not None:       # multi-GPU: the kernel stores the result rows into every rank's gather buffer (fancy_gym_b200/dist)
+            io.peer_bufs, io.n_peers, io.peer_offset = peer.next_launch()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib.fg_rollout(h, C.byref(io), B, int(T if seg_steps is None else seg_steps), C.c_void_p(stream)))
 

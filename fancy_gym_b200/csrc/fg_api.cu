@@ -196,6 +196,8 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
   if (B == 0) return FG_OK;
   if (seg_steps < 1 || seg_steps > h->cfg.n_steps)
     return fail(FG_ERR_INVALID, "fg_rollout: seg_steps %d outside 1..%d", seg_steps, h->cfg.n_steps);
+  if (io->n_peers < 0 || (io->n_peers > 0 && (!io->peer_bufs || io->peer_offset < 0 || io->n_plans > 1)))
+    return fail(FG_ERR_INVALID, "fg_rollout: peer gather needs peer_bufs, a non-negative offset and one plan per launch");
   if (io->n_plans > 1) {       // plans looped inside the launch: the handle's tables hold every plan's rows
     if (io->n_plans > FG_MAX_PLANS) return fail(FG_ERR_INVALID, "fg_rollout: n_plans %d > FG_MAX_PLANS", io->n_plans);
     if (h->cfg.mp_kind == FG_MP_TRAJ || io->seg_steps_env || io->dbg_actions || io->dbg_obs || io->dbg_rewards || io->dbg_state)

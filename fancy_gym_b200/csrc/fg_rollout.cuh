@@ -303,13 +303,28 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     }
   };
 
+  // ---- the multi-GPU gather, fused: this env's result row goes straight into every peer's gather buffer (NVLink stores;
+  // ---- the block layout is that of a contiguous result block: return f64 [B] | length i32 [B] | flags u8 [B] | 4 x u8 [B]) ----
+  auto peer_store = [&](double r_, int len_, unsigned char f_) {
+    for (int r = 0; r < io.n_peers; ++r) {
+      unsigned char* base = static_cast<unsigned char*>(io.peer_bufs[r]) + io.peer_offset;
+      reinterpret_cast<double*>(base)[b] = r_;
+      reinterpret_cast<int*>(base + 8 * B)[b] = len_;
+      base[12 * B + b] = f_;
+      base[13 * B + b] = (f_ & FG_FLAG_TERMINATED) != 0;
+      base[14 * B + b] = (f_ & FG_FLAG_TRUNCATED) != 0;
+      base[15 * B + b] = (f_ & FG_FLAG_SUCCESS) != 0;
+      base[16 * B + b] = (f_ & FG_FLAG_COLLIDED) != 0;
+    }
+  };
   // ---- results of plan kk of this env (what one step() call of the reference returns) ----
   auto write_plan_outputs = [&](int kk, int len, unsigned f, const float* obs, double i0, double i1) {
     const long long o = (long long)kk * B + b;
     io.ret[o] = ret;
     io.length[o] = len;
-    io.flags[o] = ((f & kSlotTerminated) ? FG_FLAG_TERMINATED : 0u) | ((f & kSlotTruncated) ? FG_FLAG_TRUNCATED : 0u) |
-                  ((f & kSlotSuccess) ? FG_FLAG_SUCCESS : 0u) | ((f & kSlotCollided) ? FG_FLAG_COLLIDED : 0u);
+    const unsigned char fbyte = ((f & kSlotTerminated) ? FG_FLAG_TERMINATED : 0u) | ((f & kSlotTruncated) ? FG_FLAG_TRUNCATED : 0u) |
+                                ((f & kSlotSuccess) ? FG_FLAG_SUCCESS : 0u) | ((f & kSlotCollided) ? FG_FLAG_COLLIDED : 0u);
+    io.flags[o] = fbyte;
     if (io.flag_bytes) {
       unsigned char* fb = io.flag_bytes + (long long)kk * 4 * B;
       fb[b] = (f & kSlotTerminated) != 0;
@@ -317,6 +332,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       fb[2 * B + b] = (f & kSlotSuccess) != 0;
       fb[3 * B + b] = (f & kSlotCollided) != 0;
     }
+    if (io.n_peers > 0) peer_store(ret, len, fbyte);
     for (int j = 0; j < c.n_obs_out; ++j) io.obs[o * c.n_obs_out + j] = obs[c.obs_index[j]];
     io.info[o * 4 + 0] = i0;
     io.info[o * 4 + 1] = i1;
@@ -506,6 +522,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
         if (io.prev_info)
           for (int j = 0; j < 4; ++j) io.info[o * 4 + j] = io.prev_info[b * 4 + j];
       }
+      if (io.n_peers > 0) peer_store(0.0, 0, 0);
       fl = kSlotEmpty;
       return false;
     }

@@ -177,6 +177,15 @@ typedef struct fg_rollout_io {
   int32_t plan_row0[FG_MAX_PLANS];
   double* dbg_state;       /* [B, T, 2 * dof] or NULL: joint angles and velocities after every executed step (current_pos /
                               current_vel as black_box_wrapper.py:197 hands them to a state-dependent replanning_schedule) */
+  /* Multi-GPU gather fused into the rollout (one process per GPU, env shards): n_peers > 0 makes every env ALSO store its
+   * result row (return f64 | length i32 | flags u8 | 4 flag bytes, laid out as one block of B envs exactly like ret / length /
+   * flags / flag_bytes of a contiguous result block) into the buffer of every peer, straight over NVLink:
+   * peer_bufs[r] + peer_offset is where THIS rank's block lives inside rank r's gather buffer (peer-mapped device memory,
+   * e.g. torch symmetric memory; peer_bufs itself is a DEVICE array of n_peers pointers).  No collective kernel runs: the
+   * caller only orders a barrier behind the launch before the gathered blocks are read.  One plan per launch. */
+  void* const* peer_bufs;
+  int32_t n_peers;
+  int64_t peer_offset;
 } fg_rollout_io;
 
 /* Episode reset of the classic_control reachers on the device (replaces the host-side samplers
