@@ -79,7 +79,7 @@ class FgPhaseBasis(C.Structure):
         ("pc_pos", C.c_void_p), ("pc_vel", C.c_void_p), ("pc_y", C.c_void_p), ("n_pc", C.c_int32),
         ("scaled_dt", C.c_float), ("init_time", C.c_float), ("scale", C.c_double * 17),
         ("n_steps_env", C.c_void_p), ("times_table", C.c_void_p), ("times_stride", C.c_int32),
-        ("exp_right_clip", C.c_int32), ("basis_scale", C.c_double),
+        ("exp_right_clip", C.c_int32), ("basis_scale", C.c_double), ("eval_f64", C.c_int32),
     ]
 
 

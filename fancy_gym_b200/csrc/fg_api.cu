@@ -274,7 +274,8 @@ fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const f
   memset(&a, 0, sizeof(a));
   a.mp_kind = h->cfg.mp_kind; a.N = h->cfg.n_dof; a.T = h->cfg.n_steps; a.K = h->cfg.n_basis;
   a.phase_kind = pb->phase_kind; a.n_total = pb->n_basis_total; a.first = pb->first_learnable; a.alpha_phase = pb->alpha_phase;
-  a.exp_right_clip = pb->exp_right_clip; a.basis_scale = pb->basis_scale;
+  a.exp_right_clip = pb->exp_right_clip; a.basis_scale = pb->basis_scale; a.eval_f64 = pb->eval_f64;
+  for (int k = 0; k < 16; ++k) { a.cen32[k] = (float)pb->centers[k]; a.bw32[k] = (float)pb->bandwidth[k]; }
   for (int k = 0; k < 16; ++k) { a.cen[k] = pb->centers[k]; a.bw[k] = pb->bandwidth[k]; }
   a.wscale = h->cfg.weights_scale; a.gscale = h->cfg.goal_scale; a.alpha = h->cfg.dmp_alpha; a.beta = h->cfg.dmp_alpha / 4.0f;
   a.times = times; a.dts = h->d_tab_b; a.tau = tau; a.delay = delay; a.params = params; a.bc_pos = bc_pos; a.bc_vel = bc_vel;

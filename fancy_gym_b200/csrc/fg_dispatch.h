@@ -39,6 +39,8 @@ struct PhaseArgs {
   int mp_kind, N, T, K;             // K weighted basis functions per dof
   int phase_kind, n_total, first;   // phase 0 linear / 1 exp; RBF count incl. zero padding; first weighted RBF
   int exp_right_clip;               // exponential phase of the clipped (1) or only left-bounded (0) linear phase
+  int eval_f64;                     // basis in float64 rounded once (1) or float32 elementwise like the library (0)
+  float cen32[16], bw32[16];        // float32 copies of the centres / bandwidths (eval_f64 == 0)
   double alpha_phase, basis_scale;  // basis_scale: DMP forcing-basis factor (1 unless weights_scale sits on the basis)
   double cen[16], bw[16];
   float wscale, gscale, alpha, beta;

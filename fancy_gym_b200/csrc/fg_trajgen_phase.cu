@@ -48,6 +48,29 @@ __device__ __forceinline__ double eval_basis(const PhaseArgs& a, float z, double
   return ph;
 }
 
+// The same in float32, op for op what the library's torch tensors compute (mp_pytorch NormalizedRBFBasisGenerator.basis:
+// tmp = (phase - centers)^2 * bandwidth; exp(-tmp / 2); / sum; ExpDecayPhaseGenerator.phase: exp(-alpha * z)): ~9x fewer
+// instructions than the float64 evaluation (6 expf instead of 6 double-precision exp per time point), which turns the
+// kernel from instruction bound (28 % fp64 pipe) into HBM bound.  coef[] = the float32 table entry of basis function kk.
+template <int MPK, int NT>
+__device__ __forceinline__ void eval_coef32(const PhaseArgs& a, float z, float (&coef)[NT]) {
+  const float ph = a.phase_kind ? expf(__fmul_rn(-(float)a.alpha_phase, z)) : z;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    const float d = __fsub_rn(ph, a.cen32[k]);
+    coef[k] = expf(__fmul_rn(-__fmul_rn(__fmul_rn(d, d), a.bw32[k]), 0.5f));       // (/ 2 == * 0.5 exactly)
+    sum = __fadd_rn(sum, coef[k]);
+  }
+  const float r_sum = __frcp_rn(sum);
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    if (NT > 1) coef[k] = div_by(coef[k], sum, r_sum);       // the IEEE quotient (fg_device.cuh)
+    // ProMP: basis * weights_scale; DMP: canonical x * basis (* the scale when it sits on the basis)
+    coef[k] = (MPK == FG_MP_PROMP) ? __fmul_rn(coef[k], a.wscale) : __fmul_rn(__fmul_rn(ph, coef[k]), (float)a.basis_scale);
+  }
+}
+
 // MPK: the MP type (one instantiation per type keeps the register footprint of each at its own needs);
 // NT: ProMP / DMP number of RBFs incl. zero padding; ProDMP number of weighted columns K + 1 (weights + goal)
 template <int MPK, int NT>
@@ -111,13 +134,18 @@ __global__ void __launch_bounds__(256, FG_PHASE_MINB) k_trajgen_phase(const __gr
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
       const float un = __fdiv_rn(__fsub_rn(times[t], delay), tau);       // float32 elementwise ops of the library
       const float z = fminf(fmaxf(un, 0.f), (a.phase_kind && !a.exp_right_clip) ? INFINITY : 1.f);
-      double phi[NT];
-      const double x = eval_basis<NT>(a, z, phi);
-      // coefficient of weighted basis function k = kk - first (float32, rounded once like the host-built tables)
+      // coefficient of weighted basis function k = kk - first: float32 like the library, or float64 rounded once like the
+      // host-built tables (eval_f64)
       float coef[NT];
+      if (a.eval_f64) {
+        double phi[NT];
+        const double x = eval_basis<NT>(a, z, phi);
 #pragma unroll
-      for (int kk = 0; kk < NT; ++kk)
-        coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk] * a.basis_scale);
+        for (int kk = 0; kk < NT; ++kk)
+          coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk] * a.basis_scale);
+      } else {
+        eval_coef32<MPK, NT>(a, z, coef);
+      }
       for (int d = 0; d < N; ++d) {
         float acc = 0.f;
 #pragma unroll
@@ -178,6 +206,7 @@ k_trajgen_phase_warp(const __grid_constant__ PhaseArgs a, const long long B) {
   const int T = a.n_steps_env ? min(max(a.n_steps_env[b], 2), TM) : TM;
   const float* times = a.n_steps_env ? a.times_table + (long long)T * a.times_stride : a.times;
   const float tau = a.tau[b], delay = a.delay[b];
+  const float r_tau = __frcp_rn(tau);
   for (int i = lane; i < N * KP; i += 32) {
     float p = a.params[b * N * KP + i];
     if (MPK == FG_MP_DMP) p = __fmul_rn(p, (i % KP < K) ? a.wscale : a.gscale);
@@ -233,14 +262,18 @@ k_trajgen_phase_warp(const __grid_constant__ PhaseArgs a, const long long B) {
           st_v[lane * N + d] = __fdiv_rn(av, tau);
         }
       } else if constexpr (NT <= kMaxRbf) {
-        const float un = __fdiv_rn(__fsub_rn(times[t], delay), tau);       // float32 elementwise ops of the library
+        const float un = div_by(__fsub_rn(times[t], delay), tau, r_tau);   // float32 elementwise ops of the library
         const float z = fminf(fmaxf(un, 0.f), (a.phase_kind && !a.exp_right_clip) ? INFINITY : 1.f);
-        double phi[NT];
-        const double x = eval_basis<NT>(a, z, phi);
         float coef[NT];
+        if (a.eval_f64) {
+          double phi[NT];
+          const double x = eval_basis<NT>(a, z, phi);
 #pragma unroll
-        for (int kk = 0; kk < NT; ++kk)
-          coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk] * a.basis_scale);
+          for (int kk = 0; kk < NT; ++kk)
+            coef[kk] = (MPK == FG_MP_PROMP) ? __fmul_rn((float)phi[kk], a.wscale) : (float)(x * phi[kk] * a.basis_scale);
+        } else {
+          eval_coef32<MPK, NT>(a, z, coef);
+        }
         for (int d = 0; d < N; ++d) {
           float acc = 0.f;
 #pragma unroll
@@ -253,9 +286,9 @@ k_trajgen_phase_warp(const __grid_constant__ PhaseArgs a, const long long B) {
     __syncwarp();
     if constexpr (MPK == FG_MP_PROMP) {
       if (t < T - 1 && lane < STEP) {
-        const float dtt = __fsub_rn(times[t + 1], times[t]);
+        const float dtt = __fsub_rn(times[t + 1], times[t]), r_dtt = __frcp_rn(dtt);
         for (int d = 0; d < N; ++d)
-          st_v[lane * N + d] = __fdiv_rn(__fsub_rn(st_p[(lane + 1) * N + d], st_p[lane * N + d]), dtt);
+          st_v[lane * N + d] = div_by(__fsub_rn(st_p[(lane + 1) * N + d], st_p[lane * N + d]), dtt, r_dtt);
       }
       __syncwarp();
       if (t == T - 1 && lane < STEP)                 // vel[T-1] = vel[T-2] (0 for a one-point plan: the carried row starts at 0)

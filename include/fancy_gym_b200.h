@@ -282,6 +282,9 @@ typedef struct fg_phase_basis {
   /* readings of mp_pytorch that are kept switchable (fancy_gym_b200/mp/assumptions.py; the defaults are 1 and 1.0) */
   int32_t exp_right_clip;      /* exponential phase: 1 = x = exp(-alpha * clip(z, 0, 1)), 0 = exp(-alpha * max(z, 0)) */
   double basis_scale;          /* DMP: factor on the forcing basis x * Phi (weights_scale when it is not on the parameters) */
+  int32_t eval_f64;            /* RBFs / exponential phase of ProMP and DMP: 1 = float64 rounded once to float32 (the arithmetic of
+                                  the host-built shared tables; what the Python facade passes by default), 0 = float32 elementwise
+                                  ops like the library's torch tensors (cheaper; velocities carry the library's float32 noise) */
 } fg_phase_basis;
 
 /*

@@ -13,6 +13,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.pop("FG_PHASE_F32", None)      # the record was taken with the float64 per-env basis (the default)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
