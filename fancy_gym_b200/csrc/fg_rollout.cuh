@@ -64,14 +64,13 @@ constexpr unsigned kSlotEmpty = 0u, kSlotLive = 1u, kSlotPending = 2u, kSlotStat
 constexpr unsigned kSlotTerminated = 4u, kSlotTruncated = 8u, kSlotSuccess = 16u, kSlotCollided = 32u, kSlotDeferred = 64u;
 
 // shared memory layout (32-bit words); what the step loop touches sits at compile-time addresses:
-//   [control 16 ints: want, n_live, warps bound, -, per-warp live / pending counts] [live list | pending list: 2 * BD uint16]
+//   [control words: want, n_live, warps that run, queue dry, queue base, -, -, -, per-warp live / pending counts] [live list | pending list: 2 * BD uint16]
 //   [s_m 100 (+4)] [tab_a rows * pad4(cols_a)] [tab_b rows_b * pad4(cols_b)] [1/tab_b pad4(rows_b)]
 //   [w  slots * n_dof * BD] [slot state  WORDS * BD]
-constexpr int kCtlWords = 16;
+constexpr int kCtlWords = (8 + 2 * kRolloutWarps + 15) & ~15;
 constexpr int kListWords = kRolloutThreads;            // 2 * BD uint16
 constexpr int kSmWords = (kLinePoints + 3) & ~3;
 constexpr int kFixedWords = kCtlWords + kListWords + kSmWords;
-static_assert(kRolloutWarps <= 4, "per-warp counters live in control words 8..15");
 __host__ __device__ inline size_t rollout_smem_bytes(int T, int cols_a, int rows_b, int cols_b, int w_per_thread, int slot_words,
                                                      int threads) {
   const size_t words = kFixedWords + (size_t)T * pad4(cols_a) + (size_t)rows_b * pad4(cols_b) + pad4(rows_b) +
@@ -89,7 +88,7 @@ __host__ __device__ inline size_t rollout_smem_bytes(int T, int cols_a, int rows
 template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
 __global__ void __launch_bounds__(kRolloutThreads, FG_ROLLOUT_MINB)
 k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
-          const int seg_steps, unsigned* __restrict__ queue) {
+          const int seg_steps, unsigned* __restrict__ queue, const int warps_lo, const int blocks_extra) {
   using SL = SlotLayout<ENV, MP, MOTOR, N, KC>;
   constexpr bool VF = SL::VF, VEL_ONLY = SL::VEL_ONLY;
   extern __shared__ __align__(16) float smem[];
@@ -111,6 +110,14 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   const int WS = weight_slots(MP, K);                     // slots per dof
   unsigned* sst = reinterpret_cast<unsigned*>(wsm + (HAS_W ? WS * N * BD : 0));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // The step loop polls control word 0 once per step.  Through the generic pointer every poll re-derives the shared window
+  // (S2UR SR_CgaCtaId + ULEA: ~6 % of the kernel's stall samples); the 32-bit shared address is formed once instead.
+  const unsigned ctl_saddr = (unsigned)__cvta_generic_to_shared(smem);
+  auto want_repack = [&]() -> int {
+    int v_;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v_) : "r"(ctl_saddr) : "memory");
+    return v_;
+  };
 
   // ---- stage the shared tables (coalesced reads, rows zero-padded to float4) ----
   for (int i = tid; i < RT * RA; i += BD) {
@@ -126,7 +133,10 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   for (int i = tid; i < kLinePoints; i += BD)   // float32(numpy.linspace(0,1,100)): i*(1/99) in float64, last forced to 1
     s_m[i] = (i == kLinePoints - 1) ? 1.0f : (float)((double)i * (1.0 / 99.0));
 
-  const long long b0 = (long long)blockIdx.x * BD;
+  // Envs per block: `warps_lo` warps, one more in the first `blocks_extra` blocks (the launcher uses full blocks: 4 / 0).
+  const int bi = (int)blockIdx.x;
+  const long long b0 = 32LL * ((long long)warps_lo * bi + min(bi, blocks_extra));
+  const int n_here = 32 * (warps_lo + (bi < blocks_extra ? 1 : 0));
   const int n_plans = io.n_plans > 1 ? io.n_plans : 1;
   // io.plan_T: points of ONE plan (the "last point" rules of ProMP / DMP); == c.T unless several plans share the tables
 
@@ -140,7 +150,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     wsm[(d * WS + ((MP == FG_MP_PRODMP) ? k + 2 : k)) * BD + slot] = val;
   };
   if constexpr (HAS_W) {
-    const long long nblk = min((long long)BD, B - b0);
+    const long long nblk = max(0LL, min((long long)n_here, B - b0));
     for (long long f = tid; f < nblk * P; f += BD) {
       const int th = (int)(f / P), idx = (int)(f % P);
       put_param(th, idx, io.params[(b0 + th) * PS + idx]);
@@ -571,7 +581,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   // =================================================================================================================
   {
     bool live = false;
-    if (b < B) live = start_env();
+    if (tid < n_here && b < B) live = start_env();
     const unsigned m = __ballot_sync(0xffffffffu, live);
     if (lane == 0 && m) {
       atomicAdd(const_cast<int*>(&ctl[1]), __popc(m));
@@ -594,7 +604,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     for (;;) {
       // success / collided of the last executed step (what the plan reports when its segment simply runs out)
       bool success = false, collided = false;
-      while (have && tr < tr_end && ctl[0] == 0) {
+      while (have && tr < tr_end && want_repack() == 0) {
         {
         const int t = tr;
         // ---------------------------------------------------------------- desired pos / vel at point t of the plan

@@ -30,6 +30,7 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
   // More envs than the GPU holds at once: a persistent grid (every SM full) whose threads take the next env from a work
   // queue when the one they ran is finished, instead of blocks that drain while their last envs run out.
   unsigned* q = nullptr;
+  int warps_lo = kRolloutWarps, blocks_extra = 0;
   if (queue) {
     static thread_local size_t occ_smem = ~(size_t)0;
     static thread_local int occ_blocks = 0;
@@ -43,8 +44,10 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
       blocks = resident;
       q = queue;
     }
+    // (cutting a batch that does not fill the GPU into 592 blocks of 3 or 4 warps, so that every SM holds 13 - 14 warps instead
+    //  of 12 or 16, was measured: no change — 0.259 ms either way at 65 536 envs; the warps progress at their own pace)
   }
-  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps, q);
+  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps, q, warps_lo, blocks_extra);
   return cudaGetLastError();
 }
 
