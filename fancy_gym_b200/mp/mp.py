@@ -117,7 +117,13 @@ class MPInterface:
             if not self.phase_gn.collapse_if_equal():
                 # the envs of the batch chose different taus: ragged plans.  Env b plans round(tau_b / dt) points; buffers and
                 # launches are sized for the longest admissible plan (tau_bound), the lengths stay on the device.
-                t_max = int(np.round(float(self.phase_gn.tau_bound[1]) / dt))
+                hi = float(self.phase_gn.tau_bound[1])
+                if not np.isfinite(hi):
+                    # a phase generator built without make_bb has tau_bound = [1e-5, inf]: buffers cannot be sized for an
+                    # unbounded plan length (make_bb sets [2 dt, duration] when tau is learned, make_env_helpers.py:121-126)
+                    raise ValueError("ragged sub-trajectories need a finite phase_generator_kwargs['tau_bound'] upper bound "
+                                     "(the longest plan the buffers are sized for)")
+                t_max = int(np.round(hi / dt))
                 tau = self.phase_gn.tau.to(self.device, torch.float64)
                 self.n_steps_env = torch.round(tau / dt).clamp_(2, t_max).to(torch.int32).contiguous()
                 duration = float(t_max * dt)

@@ -339,3 +339,17 @@ def test_masked_median_equals_numpy():
     got = _masked_median(torch.as_tensor(r), torch.as_tensor(L)).numpy()
     want = np.array([np.median(r[b, :L[b]]) if L[b] else 0.0 for b in range(64)])
     assert np.array_equal(got, want)
+
+
+def test_ragged_plans_need_a_finite_tau_bound():
+    """a phase generator built without make_bb has tau_bound = [1e-5, inf]: a clear ValueError instead of an OverflowError"""
+    import torch
+    from fancy_gym_b200 import mp
+    pg = mp.LinearPhaseGenerator(tau=2.0, learn_tau=True)
+    bg = mp.NormalizedRBFBasisGenerator(pg, num_basis=5)
+    tg = mp.ProMP(bg, 2, device="cpu")
+    p = torch.zeros(3, tg.num_params)
+    p[:, 0] = torch.tensor([0.3, 0.5, 0.7])
+    tg.set_params(p)
+    with pytest.raises(ValueError, match="tau_bound"):
+        tg.set_duration(None, 0.01)
