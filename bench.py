@@ -669,6 +669,34 @@ def main():
                                      workload="fancy_ProDMP/SimpleReacher-v0 x 65536, replanning t % 25, 4 plans, condition_on_desired; "
                                               "per episode batch: reset + step_plans (one fused launch for all four plans)")
             del e4, acts
+        if world == 1:
+            # learned tau / delay per env: the per-env basis evaluated inside the rollout, and the
+            # two-kernel path it replaces (fg_trajgen_phase -> [B, T, dof] trajectory in HBM -> FG_MP_TRAJ rollout)
+            et = fancy_gym.make(ENV_ID, num_envs=B, device=dev, mp_config_override={
+                "phase_generator_kwargs": {"phase_generator_type": "linear", "learn_tau": True, "learn_delay": True}})
+            pt = (args.sigma * torch.randn(B, N_PARAMS + 2, generator=gen, device=dev)).contiguous()
+            pt[:, 0] = 0.5 + 1.5 * torch.rand(B, generator=gen, device=dev)
+            pt[:, 1] = 0.3 * torch.rand(B, generator=gen, device=dev)
+            lt = {}
+            for mode, flag in (("in_rollout", "1"), ("trajgen_then_rollout", "0")):
+                os.environ["FG_PHASE_FUSED"] = flag
+                tot_t = 0
+                for i in range(3):
+                    et.reset(seed=None)
+                    et.step(pt)
+                torch.cuda.synchronize(dev)
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for i in range(20):
+                    et.reset(seed=None)
+                    tot_t = tot_t + et.step(pt)[4]["trajectory_length"].sum()
+                b_.record()
+                torch.cuda.synchronize(dev)
+                lt[mode] = agg(a_.elapsed_time(b_) / 20, int(tot_t) / 20, B)
+            os.environ.pop("FG_PHASE_FUSED", None)
+            extras["learned_tau_delay"] = dict(lt["in_rollout"], trajgen_then_rollout=lt["trajgen_then_rollout"],
+                                               workload=f"{ENV_ID} x {B} with a learned tau and delay per env; per step: reset + step()")
+            del et, pt
         # config 5: 2^20 envs per GPU (N > 1: with the per-step all-gather of every rank's results)
         B5 = 1 << 20
         e5 = fancy_gym.make(ENV_ID, num_envs=B5, device=dev, context_sampler="device", mp_config_override={"black_box_kwargs": {"result_sets": RING}})

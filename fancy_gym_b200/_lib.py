@@ -49,6 +49,7 @@ class FgRolloutIO(C.Structure):
         ("dbg_actions", C.c_void_p), ("dbg_obs", C.c_void_p), ("dbg_rewards", C.c_void_p), ("flag_bytes", C.c_void_p), ("seg_steps_env", C.c_void_p), ("prev_obs", C.c_void_p), ("prev_info", C.c_void_p), ("keep_state", C.c_int32),
         ("n_plans", C.c_int32), ("plan_T", C.c_int32), ("plan_seg", C.c_int32 * FG_MAX_PLANS), ("plan_row0", C.c_int32 * FG_MAX_PLANS),
         ("dbg_state", C.c_void_p), ("peer_bufs", C.c_void_p), ("n_peers", C.c_int32), ("peer_offset", C.c_int64),
+        ("phase", C.c_void_p), ("phase_tau", C.c_void_p), ("phase_delay", C.c_void_p), ("phase_times", C.c_void_p),
     ]
 
 

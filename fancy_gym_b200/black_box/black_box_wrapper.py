@@ -365,6 +365,11 @@ class BlackBoxWrapper(Wrapper):
         B = self.num_envs
         T = self.traj_gen.n_steps
         per_env_phase = not self.traj_gen.phase_gn.uniform()
+        fused_phase = per_env_phase and trajectory is None and dbg is None and self._phase_fusable()
+        if fused_phase:
+            # learned tau / delay differ per env and the shape is one the rollout kernel evaluates itself (fg_rollout_io.phase):
+            # the basis row of every step is computed in the thread — no fg_trajgen_phase launch, no trajectory in HBM
+            per_env_phase = False
         if trajectory is not None:
             # the desired trajectory comes from the caller (an MPWrapper hook has seen / changed it): tracked from HBM
             self._traj_buf = tuple(x.to(self.device, torch.float32).contiguous() for x in trajectory)
@@ -388,6 +393,15 @@ class BlackBoxWrapper(Wrapper):
         io.ctx = st.ctx.data_ptr()
         io.q, io.v, io.steps, io.done = st.q.data_ptr(), st.v.data_ptr(), st.steps.data_ptr(), st.done.data_ptr()
         io.keep_state = int(bool(keep_state))
+        if fused_phase:
+            tg = self.traj_gen
+            pb = tg._phase_basis()
+            tau_b, delay_b = tg.phase_gn.per_env(B, self.device)
+            keep_alive = (pb, tau_b, delay_b, tg.times_dev())
+            io.phase = C.addressof(pb)
+            io.phase_tau, io.phase_delay, io.phase_times = tau_b.data_ptr(), delay_b.data_ptr(), keep_alive[3].data_ptr()
+            if tg.n_steps_env is not None:
+                io.seg_steps_env = tg.n_steps_env.data_ptr()
         io.cond_pos, io.cond_vel = self._cond_pos.data_ptr(), self._cond_vel.data_ptr()
         io.use_cond = int(self.condition_set)
         if not per_env_phase:
@@ -508,6 +522,18 @@ class BlackBoxWrapper(Wrapper):
         if valid is not None:
             obs, ret, terminated, truncated, infos = self._merge_invalid(valid, params, trajectory, obs, ret, terminated, truncated, infos)
         return self._format(obs, ret, terminated, truncated, infos, as_numpy, scalar)
+
+    def _phase_fusable(self) -> bool:
+        """can the rollout kernel evaluate this generator's per-env phase itself?  (instantiated for the registry's shapes:
+        ProMP / DMP, 5 weighted RBFs of 5 or 6 in total with the zero padding in front, 5 or 2 links, velocity / motor control)"""
+        import os
+        tg, bg = self.traj_gen, self.traj_gen.basis_gn
+        return (os.environ.get("FG_PHASE_FUSED", "1") != "0" and not os.environ.get("FG_PHASE_F32")
+                and not getattr(tg, "per_env_basis_f32", False)
+                and tg.mp_kind in (_lib.MP_PROMP, _lib.MP_DMP) and bg.num_basis == 5 and bg.total_num_basis in (5, 6)
+                and bg.first_learnable == bg.total_num_basis - 5 and self._base.n_links in (2, 5)
+                and getattr(self.tracking_controller, "abi_code", None) in (_lib.CTRL_VELOCITY, _lib.CTRL_MOTOR)
+                and tg.phase_gn.assume["dmp_init_on_first_grid_point"])
 
     def _hooks_overridden(self) -> bool:
         """does any wrapper between this one and the step env override a trajectory hook of RawInterfaceWrapper?"""

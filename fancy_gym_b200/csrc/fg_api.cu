@@ -224,8 +224,27 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
   if (prev != h->device) FG_CUDA(cudaSetDevice(h->device));
   const char* why = nullptr;
   unsigned* queue = h->d_queue + 2 * (h->next_queue.fetch_add(1u) % kQueues);
+  fg::PhaseConst pcv;
+  const fg::PhaseConst* pc = nullptr;
+  if (io->phase) {            // per-env tau / delay evaluated inside the rollout
+    const fg_phase_basis* pb = io->phase;
+    if (pb->struct_size != sizeof(fg_phase_basis)) { if (prev != h->device) cudaSetDevice(prev); return fail(FG_ERR_INVALID, "fg_rollout: phase struct_size mismatch (ABI)"); }
+    if (!io->phase_tau || !io->phase_delay || !io->phase_times || pb->n_basis_total < 1 || pb->n_basis_total > fg::kMaxRbfFused ||
+        (pb->n_steps_env != nullptr) != (pb->times_table != nullptr) || (pb->n_steps_env && pb->times_stride < h->cfg.n_steps) ||
+        !pb->eval_f64) {
+      if (prev != h->device) cudaSetDevice(prev);
+      return fail(FG_ERR_UNSUPPORTED, "fg_rollout: per-env phase needs tau / delay / times, 1..%d RBFs and the float64 basis", fg::kMaxRbfFused);
+    }
+    memset(&pcv, 0, sizeof(pcv));
+    pcv.n_total = pb->n_basis_total; pcv.first = pb->first_learnable; pcv.phase_kind = pb->phase_kind;
+    pcv.exp_right_clip = pb->exp_right_clip; pcv.alpha_phase = pb->alpha_phase; pcv.basis_scale = pb->basis_scale;
+    for (int k = 0; k < fg::kMaxRbfFused; ++k) { pcv.cen[k] = pb->centers[k]; pcv.bw[k] = pb->bandwidth[k]; }
+    pcv.tau = io->phase_tau; pcv.delay = io->phase_delay; pcv.times = io->phase_times;
+    pcv.n_steps_env = pb->n_steps_env; pcv.times_table = pb->times_table; pcv.times_stride = pb->times_stride;
+    pc = &pcv;
+  }
   cudaError_t e = fg::launch_rollout(h->dev, h->cfg.env_kind, h->cfg.mp_kind, *io, B, seg_steps,
-                                     (cudaStream_t)stream, h->max_smem_optin, &why, queue, h->sm_count);
+                                     (cudaStream_t)stream, h->max_smem_optin, &why, queue, h->sm_count, pc);
   if (prev != h->device) cudaSetDevice(prev);
   if (why) return fail(FG_ERR_UNSUPPORTED, "fg_rollout: %s", why);
   if (e != cudaSuccess) return fail(FG_ERR_CUDA, "fg_rollout launch: %s", cudaGetErrorString(e));

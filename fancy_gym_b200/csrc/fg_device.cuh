@@ -39,6 +39,21 @@ struct DevCfg {
   int quad_rec4;            // float4 per record
 };
 
+// Per-env phase evaluated INSIDE the fused rollout (learned tau / delay: fg_rollout_io.phase): constants of the phase / basis
+// generators and the per-env inputs.  Passed by value next to DevCfg; n_total == 0: not used.
+constexpr int kMaxRbfFused = 8;
+struct PhaseConst {
+  int n_total, first, phase_kind, exp_right_clip;
+  double alpha_phase, basis_scale;
+  double cen[kMaxRbfFused], bw[kMaxRbfFused];
+  const float* tau;           // [B]
+  const float* delay;         // [B]
+  const float* times;         // [T] float32 time grid of the plan
+  const int* n_steps_env;     // ragged plans: per-env number of points, or null
+  const float* times_table;   // ragged plans: one grid row per possible length
+  int times_stride;
+};
+
 // ---- quad records of the closed-form trajectory kernel (packed on the host in fg_create) -------------------------
 //   ProMP : 5 table rows (t0 .. t0+4; the 5th feeds the finite difference of row t0+3), 4 time increments, 4 reciprocals
 //   ProDMP: 4 position rows, 4 velocity rows

@@ -8,22 +8,22 @@ namespace fg {
 
 cudaError_t launch_rollout(const DevCfg& c, int env_kind, int mp_kind, const fg_rollout_io& io, long long B,
                            int seg_steps, cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue,
-                           int sm_count) {
+                           int sm_count, const PhaseConst* pc) {
 #define FG_DOF_SWITCH(env)                                                                                          \
   switch (c.n_dof) {                                                                                                \
-    case 2: return launch_rollout_##env##_2(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);             \
-    case 3: return launch_rollout_##env##_3(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);             \
-    case 4: return launch_rollout_##env##_4(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);             \
-    case 5: return launch_rollout_##env##_5(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);             \
-    case 6: return launch_rollout_##env##_6(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);             \
-    case 7: return launch_rollout_##env##_7(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);             \
+    case 2: return launch_rollout_##env##_2(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);             \
+    case 3: return launch_rollout_##env##_3(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);             \
+    case 4: return launch_rollout_##env##_4(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);             \
+    case 5: return launch_rollout_##env##_5(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);             \
+    case 6: return launch_rollout_##env##_6(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);             \
+    case 7: return launch_rollout_##env##_7(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);             \
     default: *why = "n_links not instantiated for the fused rollout (available: 2..7)"; return cudaSuccess;         \
   }
   switch (env_kind) {
     case FG_ENV_HOLE_REACHER: FG_DOF_SWITCH(hole)
     case FG_ENV_VIAPOINT_REACHER: FG_DOF_SWITCH(viapoint)
     case FG_ENV_SIMPLE_REACHER: FG_DOF_SWITCH(simple)
-    case FG_ENV_TOY: return launch_rollout_toy(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+    case FG_ENV_TOY: return launch_rollout_toy(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
   }
 #undef FG_DOF_SWITCH
   *why = "unknown env_kind";

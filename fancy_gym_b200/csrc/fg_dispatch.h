@@ -11,7 +11,7 @@ namespace fg {
 // queue: two zeroed device words (work queue of a persistent grid, reset by the kernel itself) or null
 cudaError_t launch_rollout(const DevCfg& c, int env_kind, int mp_kind, const fg_rollout_io& io, long long B,
                            int seg_steps, cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue,
-                           int sm_count);
+                           int sm_count, const PhaseConst* pc);
 
 cudaError_t launch_trajgen(const DevCfg& c, int mp_kind, const float* params, const float* bc_pos, const float* bc_vel,
                            float* pos_out, float* vel_out, long long B, cudaStream_t stream, int max_smem_optin,
@@ -71,7 +71,8 @@ cudaError_t launch_trajgen_phase(const PhaseArgs& a, long long B, cudaStream_t s
 // per-env translation units (compiled in parallel)
 #define FG_DECL_ENV_LAUNCH(name)                                                                              \
   cudaError_t name(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,        \
-                   cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue, int sm_count)
+                   cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue, int sm_count,        \
+                   const PhaseConst* pc)
 #define FG_DECL_ENV_DOFS(env)                                                                              \
   FG_DECL_ENV_LAUNCH(launch_rollout_##env##_2); FG_DECL_ENV_LAUNCH(launch_rollout_##env##_3);                 \
   FG_DECL_ENV_LAUNCH(launch_rollout_##env##_4); FG_DECL_ENV_LAUNCH(launch_rollout_##env##_5);                 \

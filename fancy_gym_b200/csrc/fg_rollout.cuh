@@ -85,10 +85,16 @@ __host__ __device__ inline size_t rollout_smem_bytes(int T, int cols_a, int rows
 #ifndef FG_ROLLOUT_MINB
 #define FG_ROLLOUT_MINB 4   // <= 128 registers: 4 blocks of 128 threads per SM (65 536 envs need 443 resident threads per SM)
 #endif
-template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
+// NTX > 0: per-env phase (learned tau / delay): the basis row of every step is evaluated in the thread from the env's own tau /
+//          delay (NTX RBFs in total, the last KC of them weighted) instead of read from the shared tables — the arithmetic of
+//          k_trajgen_phase_warp + k_dmp_integrate_phase (fg_trajgen_phase.cu), without the 8 KB / env round trip through HBM.
+template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG, int NTX = 0>
 __global__ void __launch_bounds__(kRolloutThreads, FG_ROLLOUT_MINB)
 k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_io io, const long long B,
-          const int seg_steps, unsigned* __restrict__ queue, const int warps_lo, const int blocks_extra) {
+          const int seg_steps, unsigned* __restrict__ queue, const int warps_lo, const int blocks_extra,
+          const __grid_constant__ PhaseConst pc) {
+  static_assert(NTX == 0 || ((MP == FG_MP_PROMP || MP == FG_MP_DMP) && KC > 0 && NTX >= KC && NTX <= kMaxRbfFused),
+                "per-env phase: ProMP / DMP with register-resident weights");
   using SL = SlotLayout<ENV, MP, MOTOR, N, KC>;
   constexpr bool VF = SL::VF, VEL_ONLY = SL::VEL_ONLY;
   extern __shared__ __align__(16) float smem[];
@@ -227,6 +233,65 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   };
   const float r_tau = __frcp_rn(c.tau), r_dt = __frcp_rn(c.dt_f);
 
+  // ---- per-env phase (NTX > 0): this env's tau / delay / time grid, and the basis row of one time point -----------------
+  float tau_b = c.tau, delay_b = 0.f, r_tau_b = r_tau;
+  const float* tm = pc.times;
+  constexpr int KCC = (KC > 0) ? KC : 1;
+  auto load_phase = [&]() -> int {          // returns the number of points of this env's plan
+    int T_b = c.T;
+    if constexpr (NTX > 0) {
+      tau_b = pc.tau[b];
+      delay_b = pc.delay[b];
+      r_tau_b = __frcp_rn(tau_b);
+      if (pc.n_steps_env) {
+        T_b = min(max(pc.n_steps_env[b], 2), c.T);
+        tm = pc.times_table + (long long)T_b * pc.times_stride;
+      }
+    }
+    return T_b;
+  };
+  auto scaled_time = [&](int t_) -> float {   // left-bounded linear phase, float32 elementwise ops of the library
+    return fmaxf(div_by(__fsub_rn(tm[t_], delay_b), tau_b, r_tau_b), 0.f);
+  };
+  // coefficients of the KC weighted basis functions at time point t_: float64 phase / RBFs rounded once (exactly eval_basis of
+  // fg_trajgen_phase.cu), ProMP: * weights_scale, DMP: canonical x * basis (* the scale when it sits on the basis)
+  auto eval_row = [&](int t_, float (&coef)[KCC]) {
+    if constexpr (NTX > 0) {
+      const float un = div_by(__fsub_rn(tm[t_], delay_b), tau_b, r_tau_b);
+      const float z = fminf(fmaxf(un, 0.f), (pc.phase_kind && !pc.exp_right_clip) ? INFINITY : 1.f);
+      const double ph = pc.phase_kind ? exp(-pc.alpha_phase * (double)z) : (double)z;
+      double phi[NTX];
+      double sum = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < NTX; ++kk) {
+        const double dd = ph - pc.cen[kk];
+        phi[kk] = exp(-((dd * dd * pc.bw[kk]) / 2));
+        sum += phi[kk];
+      }
+      if (NTX > 1) {
+        const double rr = 1.0 / sum;
+#pragma unroll
+        for (int kk = 0; kk < NTX; ++kk) {
+          const double qq = phi[kk] * rr;
+          phi[kk] = fma(fma(-qq, sum, phi[kk]), rr, qq);
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < KCC; ++kk) {
+        const double f_ = phi[NTX - KCC + kk];         // the weighted functions are the last KC (zero padding in front)
+        coef[kk] = (MP == FG_MP_PROMP) ? __fmul_rn((float)f_, c.wscale) : (float)(ph * f_ * pc.basis_scale);
+      }
+    }
+  };
+  auto dot_coef = [&](const float (&coef)[KCC], int d) -> float {      // FMA chain in index order, accumulator starts at 0
+    float acc = 0.f;
+    if constexpr (KC > 0 && HAS_W) {
+#pragma unroll
+      for (int kk = 0; kk < KCC; ++kk) acc = fmaf(coef[kk], wreg[d][kk], acc);
+    }
+    return acc;
+  };
+
   // ---- the env's context (read again whenever a thread picks an env up: a few L2 hits per re-packing) ----
   auto load_context = [&]() {
     if constexpr (ENV != FG_ENV_TOY) {
@@ -258,13 +323,15 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
       for (int d = 0; d < N; ++d) {
         carry_a[d] = ybc[d];
-        carry_b[d] = __fmul_rn(vbc[d], c.tau);
+        carry_b[d] = __fmul_rn(vbc[d], tau_b);
       }
     }
     if constexpr (MP == FG_MP_PROMP) {
+      float coef0[KCC];
+      eval_row(tr, coef0);
 #pragma unroll
       for (int d = 0; d < N; ++d) {
-        carry_a[d] = dot_row(tabA + tr * RA, d, K);
+        carry_a[d] = (NTX > 0) ? dot_coef(coef0, d) : dot_row(tabA + tr * RA, d, K);
         carry_b[d] = 0.f;             // (a one-point plan has zero velocity; otherwise overwritten at the first step)
       }
     }
@@ -359,9 +426,11 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     } else {
       // the desired position is not carried through the loop in this instantiation: the same FMA chain, once, here
       const float* row = tabA + (tr - 1) * RA;
+      float coefl[KCC];
+      eval_row(tr - 1, coefl);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        lp[i] = dot_row(row, i, MP == FG_MP_PROMP ? K : K + 3);
+        lp[i] = (NTX > 0) ? dot_coef(coefl, i) : dot_row(row, i, MP == FG_MP_PROMP ? K : K + 3);
         if constexpr (MP == FG_MP_PROMP) lv[i] = carry_b[i];
         else lv[i] = div_by(dot_row(tabB + (tr - 1) * RB, i, K + 3), c.tau, r_tau);
       }
@@ -440,6 +509,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     fl = z[SL::S_FLAGS * BD];
     ret = __hiloint2double((int)z[(SL::S_RET + 1) * BD], (int)z[SL::S_RET * BD]);
     load_context();
+    load_phase();
     fetch_weights();
   };
 
@@ -452,7 +522,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     z[BD] = (unsigned)__double2hiint(a);
   };
   auto finish = [&]() {
-    const int tl = tr - (tr_last - (io.plan_T - 1));      // steps this plan executed
+    const int tl = (NTX > 0) ? tr : tr - (tr_last - (io.plan_T - 1));      // steps this plan executed
     const unsigned* za = sst + (SL::W_SCAL + SL::S_AUX) * BD + own;
     const double aux = __hiloint2double((int)za[BD], (int)za[0]);
     double ex, ey;
@@ -569,7 +639,8 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     }
     tr = io.n_plans > 1 ? io.plan_row0[0] : 0;
     tr_end = tr + plan_seg(0);
-    tr_last = tr + io.plan_T - 1;
+    const int T_b = load_phase();
+    tr_last = tr + ((NTX > 0) ? T_b : io.plan_T) - 1;
     plan_setup(ybc, vbc);
     fl = kSlotLive;
     if (tr_end <= tr) fl = kSlotPending;  // nothing to execute: reports 0 steps
@@ -613,10 +684,19 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
           for (int d = 0; d < N; ++d) pos[d] = carry_a[d];
           if (t < tr_last) {
             const float* row = tabA + (t + 1) * RA;
-            const float dtt = tabB[t * RB], rdt = tabR[t];
+            float dtt, rdt;
+            float coef[KCC];
+            if constexpr (NTX > 0) {
+              eval_row(t + 1, coef);
+              dtt = __fsub_rn(tm[t + 1], tm[t]);
+              rdt = __frcp_rn(dtt);
+            } else {
+              dtt = tabB[t * RB];
+              rdt = tabR[t];
+            }
 #pragma unroll
             for (int d = 0; d < N; ++d) {
-              const float acc = dot_row(row, d, K);
+              const float acc = (NTX > 0) ? dot_coef(coef, d) : dot_row(row, d, K);
               carry_a[d] = acc;
               carry_b[d] = div_by(__fsub_rn(acc, pos[d]), dtt, rdt);     // (pos[t+1]-pos[t]) / (times[t+1]-times[t])
             }
@@ -627,14 +707,21 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
 #pragma unroll
           for (int d = 0; d < N; ++d) {
             pos[d] = carry_a[d];
-            vel[d] = div_by(carry_b[d], c.tau, r_tau);
+            vel[d] = div_by(carry_b[d], tau_b, r_tau_b);
           }
           if (t < tr_last) {   // semi-implicit Euler in scaled time (oracle/mp.py DMP._integrate)
             const float* row = tabA + t * RA;
-            const float h = tabB[t * RB];
+            float h;
+            float coef[KCC];
+            if constexpr (NTX > 0) {
+              eval_row(t, coef);
+              h = __fsub_rn(scaled_time(t + 1), scaled_time(t));
+            } else {
+              h = tabB[t * RB];
+            }
 #pragma unroll
             for (int d = 0; d < N; ++d) {
-              const float f = dot_row(row, d, K);
+              const float f = (NTX > 0) ? dot_coef(coef, d) : dot_row(row, d, K);
               const float g = weight(d, K);
               float a = __fmul_rn(c.beta, __fsub_rn(g, carry_a[d]));
               a = __fmul_rn(c.alpha, __fsub_rn(a, carry_b[d]));

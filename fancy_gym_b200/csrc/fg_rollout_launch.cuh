@@ -1,13 +1,16 @@
 // Shared launch helper for the per-env rollout translation units.
 #pragma once
 #include "fg_dispatch.h"
+#include <cstring>
+
 #include "fg_rollout.cuh"
 
 namespace fg {
 
-template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG>
+template <int ENV, int MP, bool MOTOR, int N, int KC, bool DBG, int NTX = 0>
 cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                      int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
+                      int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0,
+                      const PhaseConst* pc = nullptr) {
   const int pw = N * weight_slots(MP, c.K);
   const size_t smem = rollout_smem_bytes(c.T, c.cols_a, c.rows_b, c.cols_b, pw, SlotLayout<ENV, MP, MOTOR, N, KC>::WORDS,
                                          kRolloutThreads);
@@ -15,7 +18,7 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
     *why = "tables + per-env weights and state exceed the shared memory of one SM (reduce n_steps or n_basis)";
     return cudaSuccess;
   }
-  auto kern = k_rollout<ENV, MP, MOTOR, N, KC, DBG>;
+  auto kern = k_rollout<ENV, MP, MOTOR, N, KC, DBG, NTX>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -47,41 +50,60 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
     // (cutting a batch that does not fill the GPU into 592 blocks of 3 or 4 warps, so that every SM holds 13 - 14 warps instead
     //  of 12 or 16, was measured: no change — 0.259 ms either way at 65 536 envs; the warps progress at their own pace)
   }
-  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps, q, warps_lo, blocks_extra);
+  PhaseConst pcv;
+  if (pc) pcv = *pc; else memset(&pcv, 0, sizeof(pcv));
+  kern<<<(unsigned)blocks, kRolloutThreads, smem, stream>>>(c, iok, B, seg_steps, q, warps_lo, blocks_extra, pcv);
   return cudaGetLastError();
 }
 
 template <int ENV, int MP, bool MOTOR, int N, int KC>
 cudaError_t launch_kc(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                      int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
+                      int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0,
+                      const PhaseConst* pc = nullptr) {
   // the per-step debug outputs of verbose >= 2 are a separate instantiation: the hot variant carries none of their code.
   // They always use run-time K (KC = 0) to keep the number of instantiations down.
   if (io.dbg_actions || io.dbg_obs || io.dbg_rewards || io.dbg_state)
-    return launch_dbg<ENV, MP, MOTOR, N, 0, true>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
-  return launch_dbg<ENV, MP, MOTOR, N, KC, false>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+    return launch_dbg<ENV, MP, MOTOR, N, 0, true>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
+  return launch_dbg<ENV, MP, MOTOR, N, KC, false>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
 }
 
 template <int ENV, int MP, bool MOTOR, int N>
 cudaError_t launch_one(const DevCfg& c, const fg_rollout_io& io, long long B, int seg_steps, cudaStream_t stream,
-                       int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
+                       int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0,
+                      const PhaseConst* pc = nullptr) {
   // num_basis = 5 is the registry default of every MP type (registry.py:76-125): register-resident weights
   // (instantiated for the registered link counts only — 5 links, SimpleReacher's 2 — to keep the library small)
+  if (pc && pc->n_total > 0) {
+    // per-env phase evaluated inside the rollout: instantiated for the registry's shapes (5 weighted RBFs of 5 or 6 in total,
+    // 5 or 2 links, velocity / motor control); everything else goes through fg_trajgen_phase + FG_MP_TRAJ
+    if constexpr ((MP == FG_MP_PROMP || MP == FG_MP_DMP) && (N == 5 || N == 2)) {
+      const bool ok = c.K == 5 && (MOTOR || c.ctrl == FG_CTRL_VELOCITY) && pc->first == pc->n_total - 5 &&
+                      !(io.dbg_actions || io.dbg_obs || io.dbg_rewards || io.dbg_state) && io.n_plans <= 1;
+      if (ok && pc->n_total == 5)
+        return launch_dbg<ENV, MP, MOTOR, N, 5, false, 5>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
+      if (ok && pc->n_total == 6)
+        return launch_dbg<ENV, MP, MOTOR, N, 5, false, 6>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
+    }
+    *why = "per-env phase inside the rollout is not instantiated for this shape (use fg_trajgen_phase + FG_MP_TRAJ)";
+    return cudaSuccess;
+  }
   if constexpr (MP != FG_MP_TRAJ && (N == 5 || N == 2)) {
     // (without a motor law the KC instantiation assumes velocity control: position control takes the run-time-K variant)
     if (c.K == 5 && (MOTOR || c.ctrl == FG_CTRL_VELOCITY))
-      return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+      return launch_kc<ENV, MP, MOTOR, N, 5>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
   }
-  return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+  return launch_kc<ENV, MP, MOTOR, N, 0>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
 }
 
 template <int ENV, int N>
 cudaError_t launch_mp_ctrl(const DevCfg& c, int mp_kind, const fg_rollout_io& io, long long B, int seg_steps,
-                           cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0) {
+                           cudaStream_t stream, int max_smem_optin, const char** why, unsigned* queue = nullptr, int sm_count = 0,
+                      const PhaseConst* pc = nullptr) {
   const bool motor = c.ctrl == FG_CTRL_MOTOR;
 #define FG_CASE(MPK)                                                                                             \
   case MPK:                                                                                                      \
-    return motor ? launch_one<ENV, MPK, true, N>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count)  \
-                 : launch_one<ENV, MPK, false, N>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+    return motor ? launch_one<ENV, MPK, true, N>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc)  \
+                 : launch_one<ENV, MPK, false, N>(c, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
   switch (mp_kind) {
     FG_CASE(FG_MP_PROMP)
     FG_CASE(FG_MP_DMP)

@@ -2,6 +2,6 @@
 #include "fg_rollout_launch.cuh"
 namespace fg {
 FG_DECL_ENV_LAUNCH(launch_rollout_simple_4) {
-  return launch_mp_ctrl<FG_ENV_SIMPLE_REACHER, 4>(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count);
+  return launch_mp_ctrl<FG_ENV_SIMPLE_REACHER, 4>(c, mp_kind, io, B, seg_steps, stream, max_smem_optin, why, queue, sm_count, pc);
 }
 }  // namespace fg

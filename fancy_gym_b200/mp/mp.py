@@ -151,6 +151,14 @@ class MPInterface:
     def times32(self) -> np.ndarray:
         return time_grid32(self.duration, self.dt, self.init_time)
 
+    def times_dev(self) -> torch.Tensor:
+        """the plan's float32 time grid on the device (cached per plan)"""
+        key = (self.n_steps, self.dt, float(np.float32(self.init_time)), str(self.device))
+        if getattr(self, "_td_key", None) != key:
+            self._td = torch.as_tensor(self.times32(), device=self.device)
+            self._td_key = key
+        return self._td
+
     def tables(self) -> MPTables:
         raise NotImplementedError
 

@@ -123,6 +123,8 @@ typedef struct fg_config {
   const float* tab_b;
 } fg_config;
 
+struct fg_phase_basis;
+
 /* Buffers of one fused-rollout launch.  DEVICE pointers.  B = number of envs. */
 typedef struct fg_rollout_io {
   uint32_t struct_size;
@@ -186,6 +188,16 @@ typedef struct fg_rollout_io {
   void* const* peer_bufs;
   int32_t n_peers;
   int64_t peer_offset;
+  /* Per-env learned tau / delay evaluated INSIDE the rollout (no fg_trajgen_phase launch, no [B, T, dof] trajectory in HBM):
+   * phase = HOST pointer to the generator constants (as for fg_trajgen_phase; its n_steps_env / times_table give ragged plans),
+   * phase_tau / phase_delay [B] float32 and phase_times [T] float32 DEVICE pointers.  The handle is the ProMP / DMP handle of the
+   * generator (its tables are not read).  Instantiated for the registry's shapes — 5 weighted RBFs of 5 or 6 in total (zero
+   * padding in front), 5 or 2 links, velocity / motor control, no per-step buffers; FG_ERR_UNSUPPORTED otherwise (use
+   * fg_trajgen_phase and a FG_MP_TRAJ handle).  Same arithmetic as fg_trajgen_phase with eval_f64 = 1: bit-identical results. */
+  const struct fg_phase_basis* phase;
+  const float* phase_tau;
+  const float* phase_delay;
+  const float* phase_times;
 } fg_rollout_io;
 
 /* Episode reset of the classic_control reachers on the device (replaces the host-side samplers
@@ -256,7 +268,8 @@ fg_status fg_trajgen(const fg_handle* h, const float* params, const float* bc_po
 /* Phase / basis generator constants for trajectory generation with a PER-ENV phase (learned tau / delay,
  * phase_generator_kwargs learn_tau / learn_delay; mp_pytorch phase_gn + basis_gn).  RBFs: exp(-(phase - center)^2 * bandwidth / 2),
  * normalised over all n_basis_total functions; only [first_learnable, first_learnable + n_basis) carry weights (zero padding). */
-typedef struct fg_phase_basis {
+typedef struct fg_phase_basis fg_phase_basis;
+struct fg_phase_basis {
   uint32_t struct_size;
   int32_t phase_kind;          /* 0 = linear, 1 = exponential decay exp(-alpha_phase * z) */
   double alpha_phase;
@@ -285,7 +298,7 @@ typedef struct fg_phase_basis {
   int32_t eval_f64;            /* RBFs / exponential phase of ProMP and DMP: 1 = float64 rounded once to float32 (the arithmetic of
                                   the host-built shared tables; what the Python facade passes by default), 0 = float32 elementwise
                                   ops like the library's torch tensors (cheaper; velocities carry the library's float32 noise) */
-} fg_phase_basis;
+};
 
 /*
  * fg_trajgen with per-env tau / delay: the basis is evaluated in the kernel (ProMP, DMP) or looked up per env in the

@@ -265,3 +265,51 @@ def test_vector_env_applies_the_learned_tau_of_every_new_episode():
         outs.append(env.evaluate(w)[1].clone())
         assert float(env.traj_gen.phase_gn.tau.reshape(-1)[0]) == tau
     assert not torch.equal(outs[0], outs[1])
+
+
+# ---- per-env learned tau / delay evaluated inside the rollout (fg_rollout_io.phase) ---------------------------------------
+FUSED_PHASE_CASES = [
+    ("fancy_ProMP/HoleReacher-v0", {"phase_generator_kwargs": dict(phase_generator_type="linear", learn_tau=True, learn_delay=True)}, {}),
+    ("fancy_ProMP/HoleReacher-v0", {"phase_generator_kwargs": dict(phase_generator_type="linear", learn_delay=True)}, {}),
+    ("fancy_DMP/ViaPointReacher-v0", {"phase_generator_kwargs": dict(phase_generator_type="exp", alpha_phase=2, learn_tau=True)}, {}),
+    ("fancy_DMP/HoleReacher-v0", {"phase_generator_kwargs": dict(phase_generator_type="exp", alpha_phase=2.5, learn_tau=True, learn_delay=True)}, {}),
+    ("fancy_ProMP/SimpleReacher-v0", {"phase_generator_kwargs": dict(phase_generator_type="linear", learn_tau=True)}, {}),
+    ("fancy_DMP/LongSimpleReacher-v0", {"phase_generator_kwargs": dict(phase_generator_type="exp", alpha_phase=2, learn_tau=True)}, {}),
+    ("fancy_ProMP/HoleReacher-v0", {}, {"learn_sub_trajectories": True}),
+    ("fancy_DMP/ViaPointReacher-v0", {}, {"learn_sub_trajectories": True, "condition_on_desired": True}),
+]
+
+
+@pytest.mark.parametrize("env_id,over,bbk", FUSED_PHASE_CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(FUSED_PHASE_CASES)])
+def test_phase_inside_the_rollout_equals_trajgen_then_rollout(env_id, over, bbk, monkeypatch):
+    """the basis of a per-env phase evaluated by the rollout thread itself == fg_trajgen_phase writing the trajectory to HBM and
+    a FG_MP_TRAJ rollout reading it back: bit for bit, incl. ragged sub-trajectory plans and condition_on_desired"""
+    import fancy_gym_b200 as fancy_gym
+    B = 1000 + 7
+    cfg = dict(over)
+    if bbk:
+        cfg["black_box_kwargs"] = dict(bbk)
+    fused = fancy_gym.make(env_id, num_envs=B, device=DEV, mp_config_override=cfg)
+    split = fancy_gym.make(env_id, num_envs=B, device=DEV, mp_config_override=cfg)
+    assert fused._phase_fusable()
+    fused.reset(seed=9); split.reset(seed=9)
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    P = fused.action_space.shape[0]
+    n_calls = 4 if bbk else 1
+    for call in range(n_calls):
+        p = 0.4 * torch.randn(B, P, generator=gen, device=DEV)
+        ph = over.get("phase_generator_kwargs", {})
+        i = 0
+        if ph.get("learn_tau") or bbk:
+            p[:, i] = (0.05 + 0.9 * torch.rand(B, generator=gen, device=DEV)) if bbk else (0.3 + 2.0 * torch.rand(B, generator=gen, device=DEV))
+            i += 1
+        if ph.get("learn_delay"):
+            p[:, i] = 0.5 * torch.rand(B, generator=gen, device=DEV)
+        monkeypatch.setenv("FG_PHASE_FUSED", "1")
+        a = fused.step(p)
+        monkeypatch.setenv("FG_PHASE_FUSED", "0")
+        b = split.step(p)
+        assert torch.equal(a[4]["trajectory_length"], b[4]["trajectory_length"]), call
+        assert torch.equal(a[0], b[0]) and _eq(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), call
+        assert torch.equal(fused.unwrapped.q, split.unwrapped.q) and torch.equal(fused.unwrapped.v, split.unwrapped.v)
+    assert fused._traj_buf is None and split._traj_buf is not None        # the fused env never materialised a trajectory
