@@ -18,6 +18,8 @@ cap rollout_sigma1 k_rollout 3 python tools/run_kernel.py rollout_sigma1
 cap rollout_1m k_rollout 2 python tools/run_kernel.py rollout_1m
 cap rollout_viapoint_dmp k_rollout 2 python tools/run_kernel.py rollout_config3
 cap rollout_simple_prodmp_plans k_rollout 2 python tools/run_kernel.py rollout_config4_plans
+cap rollout_learned_tau k_rollout 2 python tools/run_kernel.py rollout_learned_tau
+cap rollout_1m_sigma1 k_rollout 2 python tools/run_kernel.py rollout_1m_sigma1
 cap trajgen_promp k_trajgen_closed 3 python tools/run_kernel.py trajgen_promp
 cap trajgen_prodmp k_trajgen_closed 3 python tools/run_kernel.py trajgen_prodmp
 cap trajgen_dmp k_trajgen_dmp 3 python tools/run_kernel.py trajgen_dmp

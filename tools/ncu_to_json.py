@@ -14,6 +14,8 @@ SOURCES = {
     "rollout_config2": "r2_rollout_ncu_summary.txt",
     "rollout_config2_sigma1": "r2_rollout_sigma1_ncu_summary.txt",
     "rollout_config5_1m_envs": "r2_rollout_1m_envs_ncu_summary.txt",
+    "rollout_1m_envs_sigma1": "r2_rollout_1m_sigma1_ncu_summary.txt",
+    "rollout_learned_tau_delay": "r2_rollout_learned_tau_ncu_summary.txt",
     "rollout_config3_viapoint_dmp": "r2_rollout_viapoint_dmp_ncu_summary.txt",
     "rollout_config4_simple_prodmp_plans": "r2_rollout_simple_prodmp_plans_ncu_summary.txt",
     "trajgen_promp": "r2_trajgen_promp_ncu_summary.txt",

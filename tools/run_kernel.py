@@ -1,6 +1,6 @@
 """GPU: launches ONE named workload a few times so that `ncu -k regex:<kernel> -s <skip> -c 1` can capture its kernel.
     python tools/run_kernel.py <workload>
-workloads: rollout_sigma1 rollout_1m rollout_config3 rollout_config4_plans trajgen_promp trajgen_prodmp trajgen_dmp
+workloads: rollout_sigma1 rollout_learned_tau rollout_1m_sigma1 rollout_1m rollout_config3 rollout_config4_plans trajgen_promp trajgen_prodmp trajgen_dmp
            trajgen_phase_promp trajgen_phase_dmp reset cov"""
 import os
 import sys
@@ -44,6 +44,16 @@ def trajgen(env_id, phase=None, B=1 << 18):
 
 if what == "rollout_sigma1":
     rollout("fancy_ProMP/HoleReacher-v0", 65536, 1.0)
+elif what == "rollout_learned_tau":
+    over = {"phase_generator_kwargs": {"phase_generator_type": "linear", "learn_tau": True, "learn_delay": True}}
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=65536, device=dev, mp_config_override=over)
+    p = 0.25 * torch.randn(65536, 27, generator=gen, device=dev)
+    p[:, 0] = 0.5 + 1.5 * torch.rand(65536, generator=gen, device=dev)
+    p[:, 1] = 0.3 * torch.rand(65536, generator=gen, device=dev)
+    for i in range(REPS):
+        env.reset(seed=i)
+        env.step(p)
+    torch.cuda.synchronize()
 elif what == "rollout_1m_sigma1":
     rollout("fancy_ProMP/HoleReacher-v0", 1 << 20, 1.0)
 elif what == "rollout_1m":
