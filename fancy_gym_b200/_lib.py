@@ -90,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "fg_rollout", "fg_trajgen", "fg_trajgen_phase", "fg_reset", "fg_traj_cov", "fg_traj_cov_work_floats", "fg_ffma_probe",
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfancygym_b200.so")
+LIB_PATH = os.environ.get("FG_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfancygym_b200.so")
 
 
 class LibraryMissingError(ImportError):

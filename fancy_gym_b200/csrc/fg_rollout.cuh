@@ -16,6 +16,9 @@
 // thread runs never changes what is computed for that env: results are bit-identical to one-thread-per-env execution
 // (tests/test_gpu_digests.py).
 #pragma once
+#ifdef FG_ROLLOUT_CHECK
+#include <cstdio>
+#endif
 #include "fg_device.cuh"
 
 namespace fg {
@@ -75,6 +78,9 @@ __host__ __device__ inline size_t rollout_smem_bytes(int T, int cols_a, int rows
                                                      int threads) {
   const size_t words = kFixedWords + (size_t)T * pad4(cols_a) + (size_t)rows_b * pad4(cols_b) + pad4(rows_b) +
                        (size_t)w_per_thread * threads + (size_t)slot_words * threads;
+#ifdef FG_ROLLOUT_CHECK
+  return (words + 3 * (size_t)threads) * sizeof(float);
+#endif
   return words * sizeof(float);
 }
 
@@ -124,6 +130,18 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v_) : "r"(ctl_saddr) : "memory");
     return v_;
   };
+
+#ifdef FG_ROLLOUT_CHAOS
+  // test build: random per-lane / per-warp delays at every scheduling point (tools/race_probe.py, profiles/README.md "Sanitizer")
+  unsigned chaos_state = (unsigned)clock64() * 2654435761u + (blockIdx.x * BD + tid) * 40503u + 12345u;
+  auto chaos = [&](unsigned one_in, unsigned max_ns) {
+    chaos_state = chaos_state * 1664525u + 1013904223u;
+    if (((chaos_state >> 16) % one_in) == 0) __nanosleep((chaos_state >> 8) % max_ns);
+  };
+#define FG_CHAOS(a, b) chaos(a, b)
+#else
+#define FG_CHAOS(a, b)
+#endif
 
   // ---- stage the shared tables (coalesced reads, rows zero-padded to float4) ----
   for (int i = tid; i < RT * RA; i += BD) {
@@ -668,6 +686,14 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
   __syncthreads();
 
   // =================================================================================================================
+#ifdef FG_ROLLOUT_NAMED_BARRIERS
+#define FG_BAR(id) asm volatile("bar.sync " #id ", %0;" ::"n"(kRolloutThreads) : "memory")
+#else
+#define FG_BAR(id) __syncthreads()
+#endif
+#ifdef FG_ROLLOUT_CHECK
+  int rnd = 0;
+#endif
   for (;;) {
     // ------------------------------------------------------------------ run until the block wants to re-pack
     // (a lane whose env stops leaves the loop and waits for its warp; a warp without a running lane goes straight to the
@@ -676,6 +702,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       // success / collided of the last executed step (what the plan reports when its segment simply runs out)
       bool success = false, collided = false;
       while (have && tr < tr_end && want_repack() == 0) {
+        FG_CHAOS(16, 4000);
         {
         const int t = tr;
         // ---------------------------------------------------------------- desired pos / vel at point t of the plan
@@ -992,7 +1019,9 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       }
       // ---- the lanes of the warp are together again.  A plan whose segment ran out: a re-planning break
       // (black_box_wrapper.py:197-203: this plan's results, then the next plan) or the end of this launch for the env
+      FG_CHAOS(2, 20000);
       if (!(have && tr >= tr_end)) break;
+      FG_CHAOS(2, 20000);
       fl = kSlotLive | (success ? kSlotSuccess : 0u) | (collided ? kSlotCollided : 0u);
       if (k + 1 < n_plans) {
         double ex, ey;
@@ -1034,15 +1063,42 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     }
 
     // ------------------------------------------------------------------ re-pack (block-uniform)
+    FG_CHAOS(2, 50000);
     if (bound) park();
-    __syncthreads();                      // every env of the block is in its slot; nobody reads the control words any more
+    FG_CHAOS(2, 50000);
+#ifdef FG_ROLLOUT_CHECK
+    int* chk = reinterpret_cast<int*>(sst + SL::WORDS * BD);
+    chk[tid] = rnd;
+#endif
+    FG_BAR(1);                            // every env of the block is in its slot; nobody reads the control words any more
+#ifdef FG_ROLLOUT_CHECK
+    for (int w = 0; w < kRolloutWarps; ++w)
+      if (chk[w * 32 + lane] != rnd)
+        printf("B1 skew: block %d thread %d round %d sees thread %d in round %d\n", (int)blockIdx.x, tid, rnd, w * 32 + lane, chk[w * 32 + lane]);
+#endif
+    FG_CHAOS(2, 20000);
     const unsigned st = sst[(SL::W_SCAL + SL::S_FLAGS) * BD + tid] & kSlotStatusMask;
+#ifdef FG_ROLLOUT_CHECK
+    {
+      const unsigned am = __activemask();
+      if (am != 0xffffffffu) printf("diverged at the scan: block %d thread %d activemask %08x\n", (int)blockIdx.x, tid, am);
+    }
+#endif
     const unsigned lm = __ballot_sync(0xffffffffu, st == kSlotLive), pm = __ballot_sync(0xffffffffu, st == kSlotPending);
     if (lane == 0) {
       wcount[warp] = __popc(lm);
       wcount[kRolloutWarps + warp] = __popc(pm);
     }
-    __syncthreads();
+#ifdef FG_ROLLOUT_CHECK
+    chk[BD + tid] = rnd;
+#endif
+    FG_BAR(2);
+#ifdef FG_ROLLOUT_CHECK
+    for (int w = 0; w < kRolloutWarps; ++w)
+      if (chk[BD + w * 32 + lane] != rnd)
+        printf("B2 skew: block %d thread %d round %d sees thread %d in round %d\n", (int)blockIdx.x, tid, rnd, w * 32 + lane, chk[BD + w * 32 + lane]);
+#endif
+    FG_CHAOS(2, 20000);
     int lbase = 0, pbase = 0, n_live = 0, n_pend = 0;
 #pragma unroll
     for (int w = 0; w < kRolloutWarps; ++w) {
@@ -1073,7 +1129,17 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       ctl[1] = n_live;          // (+ the envs started from the queue: added by their threads below)
       ctl[2] = 0;               // warps that run something: counted below
     }
-    __syncthreads();                      // the lists are complete
+#ifdef FG_ROLLOUT_CHECK
+    chk[2 * BD + tid] = rnd;
+#endif
+    FG_BAR(3);                            // the lists are complete
+#ifdef FG_ROLLOUT_CHECK
+    for (int w = 0; w < kRolloutWarps; ++w)
+      if (chk[2 * BD + w * 32 + lane] != rnd)
+        printf("B3 skew: block %d thread %d round %d sees thread %d in round %d\n", (int)blockIdx.x, tid, rnd, w * 32 + lane, chk[2 * BD + w * 32 + lane]);
+    rnd += 1;
+#endif
+    FG_CHAOS(2, 50000);
     have = bound = false;
     if (tid < n_live) {
       pick_up(live_list[tid]);
@@ -1081,7 +1147,9 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     } else if (BD - 1 - tid < n_fin) {
       const int j = BD - 1 - tid;
       pick_up(pend_list[j]);
+      FG_CHAOS(2, 100000);
       finish();
+      FG_CHAOS(2, 100000);
       fl = kSlotEmpty;
       const unsigned base = (unsigned)ctl[4];
       const long long nb = (long long)gridDim.x * BD + (long long)base + j;
@@ -1102,9 +1170,9 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     if (__any_sync(0xffffffffu, have) && lane == 0) atomicAdd(const_cast<int*>(&ctl[2]), 1);
     if (n_live == 0) {
       if (!(queue && n_fin > 0)) break;   // every stopped env has just been finished and nothing was started
-      // nothing was running: did the queue hand out envs?  (only in this case does anybody wait for the finishing threads)
-      __syncthreads();
-      if (ctl[1] == 0) {
+      // nothing was running: did the queue hand out envs?  (only in this case does anybody wait for the finishing threads;
+      // the vote is the barrier's own: the live counter may already be counted down again by an env that has just started)
+      if (!__syncthreads_or(have)) {
         // no: the block ends, unless an env was started that has nothing to execute (it is pending: one more pass)
         if (!__syncthreads_or(bound)) break;
         if (tid == 0) ctl[0] = 1;
@@ -1120,6 +1188,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     }
   }
 #undef WSM
+#undef FG_BAR
 }
 
 }  // namespace fg
