@@ -194,7 +194,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """`--impl reference`: the reference's CPU path (oracle port: the reference is Python with uninstalled dependencies and
     /root/reference does not travel to the GPU box) on all host cores.  One "step" is a bounded sample of the workload:
     every worker process runs 2 episodes, one env at a time like the reference.  Rank 0 only."""
@@ -224,7 +224,7 @@ def run_reference(args, rank, world):
                                   vectorised_port_note=f"NOT the reference: the same port vectorised over {CPU_BATCH} envs per call"),
                 e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -242,8 +242,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: whatever libraries write to file descriptor 1 on the way (NCCL's
+    # "NCCL version ..." banner at communicator set-up) goes to stderr; the descriptor is restored for the final print
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import ctypes as C
@@ -258,8 +269,14 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound_cpus = []
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # one process per GPU: run on the CPUs next to this GPU, so that the pinned parameter buffers allocated below (first
+        # touch) and the per-step H2D copies of `e2e` stay on the GPU's side of the socket interconnect
+        if os.environ.get("FG_BENCH_BIND", "1") == "1":
+            from fancy_gym_b200.dist import bind_to_gpu_cpus
+            bound_cpus = bind_to_gpu_cpus(local_rank)
         dist.init_process_group("nccl", device_id=dev)
     B = args.envs_per_gpu
     K, W = args.steps, args.warmup
@@ -268,6 +285,11 @@ def main():
     # (the wrapper's default) already hides the all-gather; deeper rings (4, 8: FG_BENCH_RESULT_RING) were measured at N = 4
     # and change nothing (0.3367 ms per step each), i.e. the ranks are not waiting for each other's exchange
     RING = int(os.environ.get("FG_BENCH_RESULT_RING", "2")) if world > 1 else 2
+    # end to end: batches in flight.  One GPU: 2 (H2D 0.12 ms, rollout 0.27 ms).  Eight ranks share the host's PCIe / memory
+    # bandwidth and the H2D of a batch takes about as long as its rollout (24 GB/s per GPU with all ranks copying,
+    # tools/probe_h2d_numa.py): a third batch in flight keeps both busy (tools/probe_e2e_slots.py: 0.336 -> 0.306 ms at N = 8)
+    E2E_SLOTS = int(os.environ.get("FG_BENCH_E2E_SLOTS", "3" if world > 1 else "2"))
+    RING = max(RING, E2E_SLOTS)
     env = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device",
                          mp_config_override={"black_box_kwargs": {"result_sets": RING}})
     base = env.unwrapped
@@ -369,7 +391,8 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     total_steps.zero_()
     clk = ClockSampler(local_rank)
-    clk.__enter__()            # sampled until the end of the e2e loop (every timed region of this run)
+    clk.__enter__()            # sampled during the device-timed region (NVML queries of 8 ranks at once are kept out of the
+                               # host-timed e2e loops: they take driver locks the launches also need)
     if True:
         sync_all()
         t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
@@ -387,6 +410,8 @@ def main():
         t_end.record()
         host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K     # host time to ISSUE one step (no sync inside)
         sync_all()
+    if world > 1:
+        clk.__exit__()
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
     env_steps = int(total_steps.item())
@@ -493,9 +518,9 @@ def main():
 
     # the same calls, two batches in flight (EpisodePipeline: submit / wait, the step_async / step_wait pattern): every step
     # still copies ITS parameters from pinned host memory and ITS results back; the copies overlap the neighbouring rollouts
-    pipe = fancy_gym.EpisodePipeline(env)
-    for hp, src in zip(pipe.host_params, host_params):
-        hp.copy_(src)
+    pipe = fancy_gym.EpisodePipeline(env, slots=E2E_SLOTS)
+    for i, hp in enumerate(pipe.host_params):
+        hp.copy_(host_params[i % len(host_params)])
 
     def run_pipelined(n):
         steps, first = 0, pipe.next_slot
@@ -516,8 +541,8 @@ def main():
     p_s = time.perf_counter() - t0
     clk.__exit__()
     e2e = e2e_dict(p_s, p_steps, "fancy_gym_b200.EpisodePipeline(env).submit()/wait(): per batch reset() + H2D of the parameters "
-                   "from pinned host memory + .step() + D2H of return/length/terminated; two batches in flight, copies on their "
-                   "own streams overlap the neighbouring rollouts (e2e_sync: the same with one batch at a time)")
+                   "from pinned host memory + .step() + D2H of return/length/terminated; %d batches in flight, copies on their "
+                   "own streams overlap the neighbouring rollouts (e2e_sync: the same with one batch at a time)" % E2E_SLOTS)
     if e2e_sync["value"] > e2e["value"]:
         e2e, e2e_sync = e2e_sync, e2e
 
@@ -630,6 +655,19 @@ def main():
             ms, spl, _ = timed_launches(env, s1, 40, n_streams=2)
             extras["sigma1"]["two_batches_in_flight"] = agg(ms, spl, B)
             del s1
+            e1f = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device",
+                                 mp_config_override={"black_box_kwargs": {"result_sets": 4}})       # one result set per batch in flight
+            s1f = make_sets(e1f, B, N_PARAMS, 1.0, 8, 50_000)
+            ms, spl, _ = timed_launches(e1f, s1f, 40, n_streams=4)
+            extras["sigma1"]["four_batches_in_flight"] = agg(ms, spl, B)
+            del e1f, s1f
+            # (one batch of 65 536 at sigma = 1.0 cannot beat its longest episode: 200 dependent steps of ~1 us; the same
+            #  workload four times as wide — the tail of one launch is a quarter of the work instead of most of it)
+            e1w = fancy_gym.make(ENV_ID, num_envs=4 * B, device=dev, context_sampler="device")
+            s1w = make_sets(e1w, 4 * B, N_PARAMS, 1.0, 3, 50_000)
+            ms, spl, _ = timed_launches(e1w, s1w, 20)
+            extras["sigma1"]["envs_x4_one_launch"] = agg(ms, spl, 4 * B)
+            del e1w, s1w
             # config 3: fancy_DMP/ViaPointReacher-v0 x 262 144
             e3 = fancy_gym.make("fancy_DMP/ViaPointReacher-v0", num_envs=1 << 18, device=dev, context_sampler="device")
             s3 = make_sets(e3, 1 << 18, 30, 1.0, 3, 60_000)
@@ -749,11 +787,12 @@ def main():
                                                            "buffer over NVLink peer memory; one barrier per step on a side stream (ring of 4 slots)",
                                             "nccl-allgather": "all_gather(return,length,flags) per step, asynchronous behind the next rollouts "
                                                               "(ring of %d result sets)" % RING}[exchange["mode"]],
-                                exchange_note=exchange["note"]),
+                                exchange_note=exchange["note"],
+                                cpu_binding=(f"rank 0 bound to the {len(bound_cpus)} CPUs local to its GPU" if bound_cpus else "none")),
                     episodes_per_s=episodes_per_s, mean_episode_length=env_steps / (K * B), host_issue_ms_per_step=host_issue_ms,
                     roofline=roofline, roofline_trajgen=roofline_traj, cpu_baseline=cpu, e2e=e2e, e2e_sync=e2e_sync, e2e_graph=e2e_graph,
                     clocks=clocks, gpu_launches=K, configs=extras)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -920,7 +920,10 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
             // viapoint_reacher.py:79-107 (App. A.6-Q1/Q2: -inf start, `acc` is the action)
             if (!c.allow_self) {
               collided = joint_limits<N>(q);
-              if (may_self_intersect<N>(q)) {      // (the link directions are only needed for the pair tests)
+#ifndef FG_VIAPOINT_SCREEN
+#define FG_VIAPOINT_SCREEN 1
+#endif
+              if (!FG_VIAPOINT_SCREEN || may_self_intersect<N>(q)) {      // (the link directions are only needed for the pair tests)
                 float cs[N], sn[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) sincos_reduced(th[i], sn[i], cs[i]);

@@ -1,6 +1,7 @@
 // Shared launch helper for the per-env rollout translation units.
 #pragma once
 #include "fg_dispatch.h"
+#include <cstdlib>
 #include <cstring>
 
 #include "fg_rollout.cuh"
@@ -43,7 +44,8 @@ cudaError_t launch_dbg(const DevCfg& c, const fg_rollout_io& io, long long B, in
       occ_smem = smem;
     }
     const long long resident = (long long)occ_blocks * sm_count;
-    if (resident > 0 && blocks > 2 * resident) {
+    static const bool no_queue = getenv("FG_NO_QUEUE") != nullptr;      // (A/B measurements only)
+    if (resident > 0 && blocks > 2 * resident && !no_queue) {
       blocks = resident;
       q = queue;
     }

@@ -80,6 +80,42 @@ def gather_episode_results(ret, length, flags, total_envs: Optional[int] = None,
 
 # ---- zero-copy variant: the black-box wrapper keeps (return f64 | length i32 | flags u8) of a step in ONE contiguous
 # ---- byte block, so the per-step exchange is a single collective on that block with no packing kernels -------------
+
+def gpu_local_cpus(device_index: int):
+    """CPUs the driver reports as local to GPU `device_index` (same NUMA node / PCIe root), restricted to the CPUs this
+    process is allowed to run on; [] if NVML is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # torch's device index counts CUDA_VISIBLE_DEVICES entries; NVML counts physical devices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ent = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ent) and ent[device_index].isdigit():
+                phys = int(ent[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+    except Exception:
+        return []
+    cpus = [i * 64 + c for i, w in enumerate(words) for c in range(64) if (w >> c) & 1]
+    allowed = os.sched_getaffinity(0)
+    return sorted(c for c in cpus if c in allowed)
+
+
+def bind_to_gpu_cpus(device_index: int):
+    """One process per GPU: run this process (and, by first touch, the pinned host buffers it allocates afterwards) on the CPUs
+    next to its GPU, so that the per-step host->device copies of the MP parameters do not cross the socket interconnect.
+    Returns the CPU list it bound to, or [] if it left the affinity alone (NVML unavailable, or none of the GPU's CPUs is
+    allowed for this process, e.g. a container cpuset on the other socket)."""
+    import os
+    cpus = gpu_local_cpus(device_index)
+    if cpus:
+        os.sched_setaffinity(0, cpus)
+    return cpus
+
+
 def result_block_bytes(num_envs: int) -> int:
     """bytes of one result block (return f64 | length i32 | flags u8 | 4 unpacked flag bytes per env), padded to 16 so
     that typed views of the gathered blocks stay aligned"""

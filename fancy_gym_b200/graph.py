@@ -82,12 +82,20 @@ class EpisodePipeline:
 
     SLOTS = 2      # == the wrapper's alternating result sets: the results of batch k stay valid while batch k + 1 runs
 
-    def __init__(self, env):
+    def __init__(self, env, slots: int = 2):
+        """slots: batches in flight (2 by default).  More slots absorb copies that are as long as the rollout itself (8 ranks
+        sharing the host's PCIe bandwidth: the H2D of one batch takes about as long as its rollout); the env needs as many
+        result sets (`black_box_kwargs={'result_sets': slots}`)."""
         if env.do_replanning or env.learn_sub_trajectories:
             raise NotImplementedError("EpisodePipeline runs one plan per episode")
         if not env._fast_reset:
             raise NotImplementedError("EpisodePipeline needs the device-side reset (context_sampler='device')")
-        assert len(env._out_sets) >= self.SLOTS
+        self.SLOTS = int(slots)
+        if self.SLOTS < 2:
+            raise ValueError("EpisodePipeline needs at least 2 slots")
+        if len(env._out_sets) < self.SLOTS:
+            raise ValueError(f"{self.SLOTS} batches in flight need {self.SLOTS} result sets: make the env with "
+                             f"mp_config_override={{'black_box_kwargs': {{'result_sets': {self.SLOTS}}}}} (it has {len(env._out_sets)})")
         self.env = env
         dev = env.device
         B, P = env.num_envs, env.action_space.shape[0]

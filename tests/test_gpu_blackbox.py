@@ -289,16 +289,20 @@ def test_graphed_episode_replays_the_eager_episode(fg):
         assert torch.equal(term, e_term.cpu())
 
 
-def test_episode_pipeline_equals_sequential_steps(fg):
-    """EpisodePipeline (two batches in flight, H2D / rollout / D2H on their own streams) returns, batch for batch, what
+@pytest.mark.parametrize("slots", [2, 3, 4])
+def test_episode_pipeline_equals_sequential_steps(fg, slots):
+    """EpisodePipeline (2 - 4 batches in flight, H2D / rollout / D2H on their own streams) returns, batch for batch, what
     sequential reset() / step() calls return — including each env's context stream advancing once per batch"""
     import torch
     B = 4096
     seq = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
-    piped = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV)
+    piped = fg.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV, mp_config_override={"black_box_kwargs": {"result_sets": slots}})
     seq.reset(seed=3)
     piped.reset(seed=3)
-    pipe = fg.EpisodePipeline(piped)
+    if slots > 2:
+        with pytest.raises(ValueError):
+            fg.EpisodePipeline(seq, slots=slots)          # two result sets only
+    pipe = fg.EpisodePipeline(piped, slots=slots)
     gen = torch.Generator().manual_seed(1)
     pops = [0.5 * torch.randn(B, 25, generator=gen) for _ in range(7)]
     want = []
@@ -319,6 +323,6 @@ def test_episode_pipeline_equals_sequential_steps(fg):
         assert all(torch.equal(a, b) for a, b in zip(w, g))
     assert len({float(w[0].sum()) for w in want}) == len(pops)          # the batches differ: nothing was compared with itself
     with pytest.raises(ValueError):
-        pipe.submit(1 - pipe.next_slot)
+        pipe.submit((pipe.next_slot + 1) % pipe.SLOTS)
     with pytest.raises(RuntimeError):
         pipe.wait(0)
