@@ -331,13 +331,17 @@ static __device__ __noinline__ bool link_wall_bisect(const float* __restrict__ s
   return overlap(A, C) | overlap(Bx, C) | overlap3(Gl, Lr, D);
 }
 
+__device__ __forceinline__ bool wall_sample_hit(float x, float y, const Hole& h) {
+  return ((x < h.xl) & (y < 0.f)) | ((x > h.xr) & (y < 0.f)) | ((x > h.xl) & (x < h.xr) & (y < h.nd));
+}
+
 static __device__ __noinline__ bool link_wall_brute(const float* __restrict__ s_m, float c, float s, float X, float Y, const Hole h) {
   bool hit = false;
 #pragma unroll 4
   for (int m = 0; m < kLinePoints; ++m) {
     const float sm = s_m[m];
     const float x = fmaf(c, sm, X), y = fmaf(s, sm, Y);
-    hit |= ((x < h.xl) & (y < 0.f)) | ((x > h.xr) & (y < 0.f)) | ((x > h.xl) & (x < h.xr) & (y < h.nd));
+    hit |= wall_sample_hit(x, y, h);
   }
   return hit;
 }
@@ -361,11 +365,27 @@ __device__ __forceinline__ bool wall_collision(const float* __restrict__ s_m, co
     float X = 0.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      if (wall_mode == 2 || fminf(Ys[i], Ys[i + 1]) < ythr)
-        hit |= (wall_mode == 0) ? link_wall_search(s_m, cs[i], sn[i], X, Ys[i], h)
-               : (wall_mode == 3) ? link_wall_bisect(s_m, cs[i], sn[i], X, Ys[i], h)
+      const float Xn = fmaf(cs[i], 1.0f, X);
+      if (wall_mode == 2 || fminf(Ys[i], Ys[i + 1]) < ythr) {
+        if (wall_mode == 0) {
+          // The two ends of the link ARE samples (s_0 = 0: (X, Y_i); s_99 = 1: the next joint, the same fma), and every
+          // other sample lies between them in both coordinates (monotone in s).  So: an end that collides decides "hit"
+          // (the step an episode ends on: the lower end is below the ground next to the hole); both ends strictly inside
+          // the hole's column and not below its floor decide "no hit" (an arm reaching into the hole).  Only links that
+          // straddle an edge of the hole go through the searches.  (A NaN coordinate fails every comparison: searches.)
+          if (!hit) {
+            const float y0 = Ys[i], y1 = Ys[i + 1];
+            const bool end_hit = wall_sample_hit(X, y0, h) | wall_sample_hit(Xn, y1, h);
+            const bool inside = (fminf(X, Xn) > h.xl) & (fmaxf(X, Xn) < h.xr) & (fminf(y0, y1) >= h.nd);
+            if (end_hit) hit = true;
+            else if (!inside) hit = link_wall_search(s_m, cs[i], sn[i], X, y0, h);
+          }
+        } else {
+          hit |= (wall_mode == 3) ? link_wall_bisect(s_m, cs[i], sn[i], X, Ys[i], h)
                                   : link_wall_brute(s_m, cs[i], sn[i], X, Ys[i], h);
-      X = fmaf(cs[i], 1.0f, X);
+        }
+      }
+      X = Xn;
     }
   }
   return hit;
