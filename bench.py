@@ -105,7 +105,7 @@ class CpuReference:
         self.pool.close()
         self.pool.join()
 
-    def baseline(self, scalar_episodes_per_worker=8, vector_batches_per_worker=4):
+    def baseline(self, scalar_episodes_per_worker=32, vector_batches_per_worker=4):
         """cpu_baseline object of the bench line: ~10-30 s of CPU work in total"""
         sc = self.sample(scalar_episodes_per_worker, batch=1)
         ve = self.sample(vector_batches_per_worker, batch=CPU_BATCH)
@@ -655,12 +655,7 @@ def main():
             ms, spl, _ = timed_launches(env, s1, 40, n_streams=2)
             extras["sigma1"]["two_batches_in_flight"] = agg(ms, spl, B)
             del s1
-            e1f = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device",
-                                 mp_config_override={"black_box_kwargs": {"result_sets": 4}})       # one result set per batch in flight
-            s1f = make_sets(e1f, B, N_PARAMS, 1.0, 8, 50_000)
-            ms, spl, _ = timed_launches(e1f, s1f, 40, n_streams=4)
-            extras["sigma1"]["four_batches_in_flight"] = agg(ms, spl, B)
-            del e1f, s1f
+            # (more than two batches in flight add ~2 %: tools/probe_sigma1_streams.py)
             # (one batch of 65 536 at sigma = 1.0 cannot beat its longest episode: 200 dependent steps of ~1 us; the same
             #  workload four times as wide — the tail of one launch is a quarter of the work instead of most of it)
             e1w = fancy_gym.make(ENV_ID, num_envs=4 * B, device=dev, context_sampler="device")

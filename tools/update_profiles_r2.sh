@@ -6,6 +6,7 @@ for k in rollout rollout_sigma1 rollout_1m rollout_1m_sigma1 rollout_learned_tau
   [ -s gpurun_out/prof_${k}_$T.raw.csv ] && python profiles/ncu_summary.py gpurun_out/prof_${k}_$T.raw.csv > profiles/r2_${out}_ncu_summary.txt
   [ -s gpurun_out/prof_${k}_$T.cuda.csv ] && python profiles/src_hot.py gpurun_out/prof_${k}_$T.cuda.csv 25 > profiles/r2_${out}_hot_lines.txt
   [ -s gpurun_out/prof_${k}_$T.sass.csv ] && python profiles/sass_hist.py gpurun_out/prof_${k}_$T.sass.csv > profiles/r2_${out}_sass.txt
+  case $k in rollout*) [ -s gpurun_out/prof_${k}_$T.cuda.csv ] && python profiles/lane_loss.py gpurun_out/prof_${k}_$T.cuda.csv 20 > profiles/r2_${out}_lane_loss.txt;; esac
 done
 cp gpurun_out/launches_$T.csv profiles/r2_launches.csv
 cp gpurun_out/bench_$T.json profiles/r2_bench.json
