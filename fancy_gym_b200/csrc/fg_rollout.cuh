@@ -250,6 +250,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
     if constexpr (KC > 0) return wreg[d][kk]; else return WSM(d, kk);
   };
   const float r_tau = __frcp_rn(c.tau), r_dt = __frcp_rn(c.dt_f);
+  const double r_dt64 = __drcp_rn(c.dt);
 
   // ---- per-env phase (NTX > 0): this env's tau / delay / time grid, and the basis row of one time point -----------------
   float tau_b = c.tau, delay_b = 0.f, r_tau_b = r_tau;
@@ -800,7 +801,7 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
           if (MOTOR || steps == 0) {      // v is float64 (zeros at reset / float64 actions): float64 arithmetic
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-              const double ac = (a64[i] - (VF ? (double)vf[i] : v[i])) / c.dt;
+              const double ac = div_by64(a64[i] - (VF ? (double)vf[i] : v[i]), c.dt, r_dt64);
               acc_cost += ac * ac;
             }
           } else {                        // float32 action and float32 velocity

@@ -1,6 +1,6 @@
 """GPU: launches ONE named workload a few times so that `ncu -k regex:<kernel> -s <skip> -c 1` can capture its kernel.
     python tools/run_kernel.py <workload>
-workloads: rollout_sigma1 rollout_learned_tau rollout_1m_sigma1 rollout_1m rollout_config3 rollout_config4_plans trajgen_promp trajgen_prodmp trajgen_dmp
+workloads: rollout_hole_prodmp rollout_hole_dmp rollout_sigma1 rollout_learned_tau rollout_1m_sigma1 rollout_1m rollout_config3 rollout_config4_plans trajgen_promp trajgen_prodmp trajgen_dmp
            trajgen_phase_promp trajgen_phase_dmp reset cov"""
 import os
 import sys
@@ -58,6 +58,10 @@ elif what == "rollout_1m_sigma1":
     rollout("fancy_ProMP/HoleReacher-v0", 1 << 20, 1.0)
 elif what == "rollout_1m":
     rollout("fancy_ProMP/HoleReacher-v0", 1 << 20, 0.25)
+elif what == "rollout_hole_prodmp":
+    rollout("fancy_ProDMP/HoleReacher-v0", 65536, 0.25)
+elif what == "rollout_hole_dmp":
+    rollout("fancy_DMP/HoleReacher-v0", 65536, 0.25)
 elif what == "rollout_config3":
     rollout("fancy_DMP/ViaPointReacher-v0", 1 << 18, 1.0)
 elif what == "rollout_config4_plans":
