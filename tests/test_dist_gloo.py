@@ -112,3 +112,16 @@ def test_result_blocks_gather_world2(B):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+def test_bind_to_gpu_cpus_is_safe_without_a_gpu():
+    """one process per GPU: the rank runs on the CPUs NVML reports next to its GPU; without NVML / a GPU it leaves the
+    affinity alone and says so"""
+    import os
+    from fancy_gym_b200.dist import bind_to_gpu_cpus, gpu_local_cpus
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_cpus(0)
+    assert cpus == gpu_local_cpus(0) or set(cpus) <= before
+    after = os.sched_getaffinity(0)
+    assert after == (set(cpus) if cpus else before)
+    os.sched_setaffinity(0, before)
