@@ -522,15 +522,15 @@ def main():
     for i, hp in enumerate(pipe.host_params):
         hp.copy_(host_params[i % len(host_params)])
 
-    def run_pipelined(n):
+    def run_pipelined(n, pipe=pipe):
         steps, first = 0, pipe.next_slot
         for i in range(n):
             slot = (first + i) % pipe.SLOTS
             if i >= pipe.SLOTS:
-                steps += int(pipe.wait(slot)[1].sum())      # the caller reads the lengths (and returns) of batch i - 2
+                steps += int(pipe.wait(slot)[1].sum(dtype=torch.int64))      # the caller reads the lengths (and returns) of batch i - SLOTS
             pipe.submit(slot)
         for i in range(max(0, n - pipe.SLOTS), n):
-            steps += int(pipe.wait((first + i) % pipe.SLOTS)[1].sum())
+            steps += int(pipe.wait((first + i) % pipe.SLOTS)[1].sum(dtype=torch.int64))
         return steps
 
     run_pipelined(max(W, pipe.SLOTS))
@@ -748,7 +748,26 @@ def main():
         if world > 1:
             finish_gathers()
             env, exchange["peer"] = env_small, peer_small
-        del e5, s5
+        # ... and end to end: per batch reset + H2D of 105 MB of parameters from pinned host memory + step() + D2H of the results
+        pipe5 = fancy_gym.EpisodePipeline(e5, slots=E2E_SLOTS)
+        for i, hp in enumerate(pipe5.host_params):
+            hp.copy_(s5[i % len(s5)]["params"])
+        run_pipelined(2 * E2E_SLOTS, pipe5)
+        sync_all()
+        t0 = time.perf_counter()
+        n5 = 12
+        st5 = run_pipelined(n5, pipe5)
+        sync_all()
+        dt5 = time.perf_counter() - t0
+        t5 = torch.tensor([dt5], dtype=torch.float64, device=dev)
+        c5 = torch.tensor([float(st5)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c5, op=dist.ReduceOp.SUM)
+        extras["config5" if world > 1 else "config5_1gpu"]["e2e"] = dict(
+            value=float(c5.item()) / float(t5.item()), unit="env-steps/s", ms_per_step=1e3 * float(t5.item()) / n5,
+            h2d_bytes_per_step=B5 * N_PARAMS * 4, d2h_bytes_per_step=B5 * 13, batches_in_flight=E2E_SLOTS)
+        del pipe5, e5, s5
     except Exception as ex:      # noqa: BLE001  (extras never fail the bench line)
         extras["error"] = repr(ex)
     torch.cuda.empty_cache()
