@@ -390,6 +390,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     total_steps.zero_()
+    step_sums = torch.zeros(K, dtype=torch.int64, device=dev)
     clk = ClockSampler(local_rank)
     clk.__enter__()            # sampled during the device-timed region (NVML queries of 8 ranks at once are kept out of the
                                # host-timed e2e loops: they take driver locks the launches also need)
@@ -405,7 +406,7 @@ def main():
             env.launch(s["params"], state=s["state"], keep_state=True)
             kev[i][1].record()
             gather_results()
-            total_steps += env._len.sum()
+            torch.sum(env._len, dim=0, dtype=torch.int64, out=step_sums[i])      # the env steps of this launch: ONE small kernel
         finish_gathers()       # the last exchange is inside the timed region
         t_end.record()
         host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K     # host time to ISSUE one step (no sync inside)
@@ -414,7 +415,7 @@ def main():
         clk.__exit__()
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
-    env_steps = int(total_steps.item())
+    env_steps = int(step_sums.sum().item())
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     n = torch.tensor([float(env_steps)], dtype=torch.float64, device=dev)
     if world > 1:
