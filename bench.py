@@ -649,6 +649,10 @@ def main():
                 ms, spl, n_done = timed_launches(env, sets, 200, min_seconds=2.0)
             extras["sustained"] = dict(agg(ms, spl, B), launches=n_done, seconds=ms * n_done * 1e-3, clocks=cs.summary(),
                                        workload="BASELINE configs[1], the timed launch of `value` repeated for >= 2 s")
+            # the same launches with two batches in flight (two streams): the second batch fills the SMs the sub-wave grid of
+            # the first leaves partly empty and covers its tail (what `e2e`'s pipeline also does)
+            ms, spl, _ = timed_launches(env, sets, 100, n_streams=2)
+            extras["config2_two_batches_in_flight"] = dict(agg(ms, spl, B), workload="BASELINE configs[1], two launches in flight on two streams")
             # sigma = 1.0: most episodes end in a collision at different steps (re-packing of live envs inside the kernel)
             s1 = make_sets(env, B, N_PARAMS, 1.0, 6, 50_000)
             ms, spl, _ = timed_launches(env, s1, 40)
