@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <new>
@@ -241,6 +242,8 @@ fg_status fg_rollout(const fg_handle* h, const fg_rollout_io* io, int64_t B, int
     for (int k = 0; k < fg::kMaxRbfFused; ++k) { pcv.cen[k] = pb->centers[k]; pcv.bw[k] = pb->bandwidth[k]; }
     pcv.tau = io->phase_tau; pcv.delay = io->phase_delay; pcv.times = io->phase_times;
     pcv.n_steps_env = pb->n_steps_env; pcv.times_table = pb->times_table; pcv.times_stride = pb->times_stride;
+    const bool no_rec = getenv("FG_PHASE_NO_RECURRENCE") != nullptr;             // (A/B runs and tests: evaluate every RBF directly)
+    if (!no_rec) fg::rbf_recurrence(pcv.rec, pcv.cen, pcv.bw, pcv.n_total, pcv.phase_kind);
     pc = &pcv;
   }
   cudaError_t e = fg::launch_rollout(h->dev, h->cfg.env_kind, h->cfg.mp_kind, *io, B, seg_steps,
@@ -296,6 +299,8 @@ fg_status fg_trajgen_phase(const fg_handle* h, const fg_phase_basis* pb, const f
   a.exp_right_clip = pb->exp_right_clip; a.basis_scale = pb->basis_scale; a.eval_f64 = pb->eval_f64;
   for (int k = 0; k < 16; ++k) { a.cen32[k] = (float)pb->centers[k]; a.bw32[k] = (float)pb->bandwidth[k]; }
   for (int k = 0; k < 16; ++k) { a.cen[k] = pb->centers[k]; a.bw[k] = pb->bandwidth[k]; }
+  if (a.mp_kind == FG_MP_PROMP && a.eval_f64 && !getenv("FG_PHASE_NO_RECURRENCE"))
+    fg::rbf_recurrence(a.rec, a.cen, a.bw, a.n_total, a.phase_kind);
   a.wscale = h->cfg.weights_scale; a.gscale = h->cfg.goal_scale; a.alpha = h->cfg.dmp_alpha; a.beta = h->cfg.dmp_alpha / 4.0f;
   a.times = times; a.dts = h->d_tab_b; a.tau = tau; a.delay = delay; a.params = params; a.bc_pos = bc_pos; a.bc_vel = bc_vel;
   a.pos = pos_out; a.vel = vel_out;

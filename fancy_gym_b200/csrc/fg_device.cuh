@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+
 #include "fancy_gym_b200.h"
 
 namespace fg {
@@ -39,6 +41,88 @@ struct DevCfg {
   int quad_rec4;            // float4 per record
 };
 
+// Normalised RBFs at a LINEAR phase p: the functions of neighbouring centres differ by a ratio that is itself (almost) a
+// geometric sequence,
+//   phi_{k+1} = phi_k * r_k,   r_0 = exp(B_0 p + C_0) (1 + A_0 p^2),   r_{k+1} = r_k * q_k * (1 + (dA_k p + dB_k) p)
+// (A, B, C: the coefficients of a_{k+1}(p) - a_k(p), a_k = -bw_k (p - c_k)^2 / 2; A, dA, dB ~ 1e-14: the centres are a float64
+// linspace and every function has the bandwidth of its own spacing) — two exp() per time point instead of one per function.
+// The float64 values differ from the direct evaluation's by a few hundred ulps at most; what the MP uses are the values
+// ROUNDED TO FLOAT32, and the kernels fall back to the direct evaluation whenever a value sits within 2^12 float64 ulps of a
+// float32 rounding boundary (8e-5 of the time points), so the float32 tables are bit-identical.
+constexpr int kMaxRbfRec = 16;
+struct RbfRec {
+  int on;                     // 0: not applicable, every function is evaluated directly
+  double a0, b0, c0;
+  double q[kMaxRbfRec], da[kMaxRbfRec], db[kMaxRbfRec];
+};
+
+// host: the constants for n functions with centres cen[] and bandwidths bw[] (long double arithmetic)
+inline void rbf_recurrence(RbfRec& r, const double* cen, const double* bw, int n, int phase_kind) {
+  r.on = 0;
+  if (phase_kind != 0 || n < 3 || n > kMaxRbfRec) return;
+  long double A[kMaxRbfRec], B[kMaxRbfRec], C[kMaxRbfRec];
+  for (int k = 0; k + 1 < n; ++k) {
+    const long double b0 = bw[k], b1 = bw[k + 1], c0 = cen[k], c1 = cen[k + 1];
+    A[k] = -(b1 - b0) / 2;
+    B[k] = b1 * c1 - b0 * c0;
+    C[k] = -(b1 * c1 * c1 - b0 * c0 * c0) / 2;
+  }
+  // every exponent stays far inside the range of exp() for a phase in [0, 1] (no function under- or overflows)
+  for (int k = 0; k < n; ++k)
+    for (int e = 0; e <= 1; ++e) {
+      const long double d = (long double)e - cen[k];
+      if (!(d * d * bw[k] / 2 <= 600.0L)) return;
+    }
+  auto absl = [](long double x) { return x < 0 ? -x : x; };
+  if (!(absl(A[0]) <= 1e-9L) || !(absl(B[0]) + absl(C[0]) <= 600.0L)) return;
+  for (int k = 0; k + 2 < n; ++k) {
+    const long double dA = A[k + 1] - A[k], dB = B[k + 1] - B[k], dC = C[k + 1] - C[k];
+    if (!(absl(dA) + absl(dB) <= 1e-9L) || !(absl(dC) <= 600.0L)) return;
+    r.q[k] = (double)expl(dC);
+    r.da[k] = (double)dA;
+    r.db[k] = (double)dB;
+  }
+  r.a0 = (double)A[0];
+  r.b0 = (double)B[0];
+  r.c0 = (double)C[0];
+  r.on = 1;
+}
+
+// phi[0 .. NT) by the recurrence (phi[0] exactly as the direct evaluation), normalised like the direct evaluation; returns
+// true if one of the values phi[first .. NT) sits too close to a float32 rounding boundary (or is tiny): evaluate directly
+template <int NT>
+__device__ __forceinline__ bool rbf_recurrence_eval(const RbfRec& rc, const double* __restrict__ cen, const double* __restrict__ bw,
+                                                    double ph, int first, double (&phi)[NT]) {
+  const double d0 = ph - cen[0];
+  phi[0] = exp(-((d0 * d0 * bw[0]) / 2));
+  double r = exp(fma(rc.b0, ph, rc.c0));
+  r = fma(r, rc.a0 * ph * ph, r);
+  double sum = phi[0];
+#pragma unroll
+  for (int k = 0; k + 1 < NT; ++k) {
+    phi[k + 1] = phi[k] * r;
+    sum += phi[k + 1];
+    if (k + 2 < NT) {
+      const double rq = r * rc.q[k];
+      r = fma(rq, fma(rc.da[k], ph, rc.db[k]) * ph, rq);
+    }
+  }
+  const double rr = 1.0 / sum;
+  bool tie = false;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    const double qq = phi[k] * rr;
+    phi[k] = fma(fma(-qq, sum, phi[k]), rr, qq);
+    if (k >= first) {
+      // float32 keeps 23 of the 52 mantissa bits: round-to-nearest flips where the 29 dropped bits cross 2^28
+      const unsigned dropped = (unsigned)__double2loint(phi[k]) & 0x1FFFFFFFu;
+      tie |= (dropped - (0x10000000u - 4096u)) < 8192u;
+      tie |= !(phi[k] > 1e-30);                      // (no float32 denormals / NaN on this path)
+    }
+  }
+  return tie;
+}
+
 // Per-env phase evaluated INSIDE the fused rollout (learned tau / delay: fg_rollout_io.phase): constants of the phase / basis
 // generators and the per-env inputs.  Passed by value next to DevCfg; n_total == 0: not used.
 constexpr int kMaxRbfFused = 8;
@@ -52,6 +136,7 @@ struct PhaseConst {
   const int* n_steps_env;     // ragged plans: per-env number of points, or null
   const float* times_table;   // ragged plans: one grid row per possible length
   int times_stride;
+  RbfRec rec;                 // linear phase: two exp() per time point instead of one per RBF (rbf_recurrence())
 };
 
 // ---- quad records of the closed-form trajectory kernel (packed on the host in fg_create) -------------------------

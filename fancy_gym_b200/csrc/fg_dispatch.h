@@ -43,6 +43,7 @@ struct PhaseArgs {
   float cen32[16], bw32[16];        // float32 copies of the centres / bandwidths (eval_f64 == 0)
   double alpha_phase, basis_scale;  // basis_scale: DMP forcing-basis factor (1 unless weights_scale sits on the basis)
   double cen[16], bw[16];
+  RbfRec rec;                       // ProMP with a linear phase: two exp() per time point (fg_device.cuh)
   float wscale, gscale, alpha, beta;
   const float* times;               // [T] float32 time grid (device)
   const float* dts;                 // [T-1] its increments (ProMP velocity), device

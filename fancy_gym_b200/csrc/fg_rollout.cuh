@@ -280,19 +280,27 @@ k_rollout(const __grid_constant__ DevCfg c, const __grid_constant__ fg_rollout_i
       const float z = fminf(fmaxf(un, 0.f), (pc.phase_kind && !pc.exp_right_clip) ? INFINITY : 1.f);
       const double ph = pc.phase_kind ? exp(-pc.alpha_phase * (double)z) : (double)z;
       double phi[NTX];
-      double sum = 0.0;
-#pragma unroll
-      for (int kk = 0; kk < NTX; ++kk) {
-        const double dd = ph - pc.cen[kk];
-        phi[kk] = exp(-((dd * dd * pc.bw[kk]) / 2));
-        sum += phi[kk];
+      bool direct = true;
+      if constexpr (MP == FG_MP_PROMP && NTX >= 3) {
+        // the recurrence of fg_device.cuh (two exp() instead of NTX); a value too close to a float32 rounding boundary
+        // sends the time point through the direct evaluation below
+        if (pc.rec.on) direct = rbf_recurrence_eval<NTX>(pc.rec, pc.cen, pc.bw, ph, NTX - KCC, phi);
       }
-      if (NTX > 1) {
-        const double rr = 1.0 / sum;
+      if (direct) {
+        double sum = 0.0;
 #pragma unroll
         for (int kk = 0; kk < NTX; ++kk) {
-          const double qq = phi[kk] * rr;
-          phi[kk] = fma(fma(-qq, sum, phi[kk]), rr, qq);
+          const double dd = ph - pc.cen[kk];
+          phi[kk] = exp(-((dd * dd * pc.bw[kk]) / 2));
+          sum += phi[kk];
+        }
+        if (NTX > 1) {
+          const double rr = 1.0 / sum;
+#pragma unroll
+          for (int kk = 0; kk < NTX; ++kk) {
+            const double qq = phi[kk] * rr;
+            phi[kk] = fma(fma(-qq, sum, phi[kk]), rr, qq);
+          }
         }
       }
 #pragma unroll

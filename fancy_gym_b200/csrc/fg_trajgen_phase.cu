@@ -30,6 +30,9 @@ constexpr int kMaxRbf = 16;
 template <int NT>
 __device__ __forceinline__ double eval_basis(const PhaseArgs& a, float z, double (&phi)[NT]) {
   const double ph = a.phase_kind ? exp(-a.alpha_phase * (double)z) : (double)z;
+  if constexpr (NT >= 3) {       // ProMP, linear phase: the recurrence, unless a value is too close to a float32 rounding boundary
+    if (a.rec.on && !rbf_recurrence_eval<NT>(a.rec, a.cen, a.bw, ph, a.first, phi)) return ph;
+  }
   double sum = 0.0;
 #pragma unroll
   for (int k = 0; k < NT; ++k) {

@@ -313,3 +313,34 @@ def test_phase_inside_the_rollout_equals_trajgen_then_rollout(env_id, over, bbk,
         assert torch.equal(a[0], b[0]) and _eq(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), call
         assert torch.equal(fused.unwrapped.q, split.unwrapped.q) and torch.equal(fused.unwrapped.v, split.unwrapped.v)
     assert fused._traj_buf is None and split._traj_buf is not None        # the fused env never materialised a trajectory
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_rbf_recurrence_leaves_the_float32_basis_unchanged(fused, monkeypatch):
+    """linear phase, learned tau + delay per env: the two-exp recurrence for the normalised RBFs (with its fall-back to the
+    direct evaluation next to a float32 rounding boundary) gives, bit for bit, what evaluating every RBF directly gives —
+    inside the rollout and in the stand-alone trajectory kernel, 65 536 envs x 200 time points"""
+    import fancy_gym_b200 as fancy_gym
+    B = 65536
+    over = {"phase_generator_kwargs": {"phase_generator_type": "linear", "learn_tau": True, "learn_delay": True}}
+    env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=DEV, mp_config_override=over)
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    p = 0.3 * torch.randn(B, env.action_space.shape[0], generator=gen, device=DEV)
+    p[:, 0] = 0.3 + 2.0 * torch.rand(B, generator=gen, device=DEV)
+    p[:, 1] = 0.5 * torch.rand(B, generator=gen, device=DEV)
+    monkeypatch.setenv("FG_PHASE_FUSED", "1" if fused else "0")
+    outs = []
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv("FG_PHASE_NO_RECURRENCE", "1")
+        else:
+            monkeypatch.delenv("FG_PHASE_NO_RECURRENCE", raising=False)
+        env.reset(seed=5)
+        o = env.step(p)
+        outs.append((o[0].clone(), o[1].clone(), o[4]["trajectory_length"].clone(),
+                     None if fused else (env._traj_buf[0].clone(), env._traj_buf[1].clone())))
+    a, b = outs
+    assert torch.equal(a[2], b[2]) and torch.equal(a[0], b[0]) and _eq(a[1], b[1])
+    if not fused:
+        assert torch.equal(a[3][0], b[3][0]) and torch.equal(a[3][1], b[3][1])          # positions / velocities [B, T, dof]
+        assert float(a[3][0].abs().max()) > 0.1
