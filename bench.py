@@ -288,7 +288,11 @@ def main():
     # end to end: batches in flight.  One GPU: 2 (H2D 0.12 ms, rollout 0.27 ms).  Eight ranks share the host's PCIe / memory
     # bandwidth and the H2D of a batch takes about as long as its rollout (24 GB/s per GPU with all ranks copying,
     # tools/probe_h2d_numa.py): a third batch in flight keeps both busy (tools/probe_e2e_slots.py: 0.336 -> 0.306 ms at N = 8)
-    E2E_SLOTS = int(os.environ.get("FG_BENCH_E2E_SLOTS", "3" if world > 1 else "2"))
+    # With the rollouts of consecutive batches overlapping (one compute stream per batch in flight) and every batch replayed as
+    # two CUDA graphs, four batches in flight reach the device's two-launches-in-flight rate (tools/probe_e2e_slots.py, one
+    # GPU: 2 / 3 / 4 slots 0.233 / 0.202 / 0.182 ms per step; eager submits are host bound at 0.22 ms)
+    E2E_SLOTS = int(os.environ.get("FG_BENCH_E2E_SLOTS", "4"))
+    E2E_GRAPHS = os.environ.get("FG_BENCH_E2E_GRAPHS", "1") == "1"
     RING = max(RING, E2E_SLOTS)
     env = fancy_gym.make(ENV_ID, num_envs=B, device=dev, context_sampler="device",
                          mp_config_override={"black_box_kwargs": {"result_sets": RING}})
@@ -519,7 +523,15 @@ def main():
 
     # the same calls, two batches in flight (EpisodePipeline: submit / wait, the step_async / step_wait pattern): every step
     # still copies ITS parameters from pinned host memory and ITS results back; the copies overlap the neighbouring rollouts
-    pipe = fancy_gym.EpisodePipeline(env, slots=E2E_SLOTS)
+    def make_pipeline(e):
+        if E2E_GRAPHS:
+            try:
+                return fancy_gym.EpisodePipeline(e, slots=E2E_SLOTS, graphs=True), "two CUDA graphs per batch (reset | H2D + rollout + D2H)"
+            except Exception as ex_:      # noqa: BLE001  (capture refused: the eager pipeline measures the same calls)
+                return fancy_gym.EpisodePipeline(e, slots=E2E_SLOTS), "eager submits (graph capture failed: %r)" % (ex_,)
+        return fancy_gym.EpisodePipeline(e, slots=E2E_SLOTS), "eager submits"
+
+    pipe, pipe_mode = make_pipeline(env)
     for i, hp in enumerate(pipe.host_params):
         hp.copy_(host_params[i % len(host_params)])
 
@@ -542,8 +554,9 @@ def main():
     p_s = time.perf_counter() - t0
     clk.__exit__()
     e2e = e2e_dict(p_s, p_steps, "fancy_gym_b200.EpisodePipeline(env).submit()/wait(): per batch reset() + H2D of the parameters "
-                   "from pinned host memory + .step() + D2H of return/length/terminated; %d batches in flight, copies on their "
-                   "own streams overlap the neighbouring rollouts (e2e_sync: the same with one batch at a time)" % E2E_SLOTS)
+                   "from pinned host memory + rollout + D2H of return/length/terminated; %d batches in flight, each with its own env "
+                   "state and compute stream (copies and the rollouts of consecutive batches overlap), %s "
+                   "(e2e_sync: reset() + step() with one batch at a time)" % (E2E_SLOTS, pipe_mode))
     if e2e_sync["value"] > e2e["value"]:
         e2e, e2e_sync = e2e_sync, e2e
 
@@ -754,7 +767,7 @@ def main():
             finish_gathers()
             env, exchange["peer"] = env_small, peer_small
         # ... and end to end: per batch reset + H2D of 105 MB of parameters from pinned host memory + step() + D2H of the results
-        pipe5 = fancy_gym.EpisodePipeline(e5, slots=E2E_SLOTS)
+        pipe5, _ = make_pipeline(e5)
         for i, hp in enumerate(pipe5.host_params):
             hp.copy_(s5[i % len(s5)]["params"])
         run_pipelined(2 * E2E_SLOTS, pipe5)

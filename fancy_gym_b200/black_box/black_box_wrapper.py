@@ -446,7 +446,30 @@ class BlackBoxWrapper(Wrapper):
         self.traj_gen.reset()       # every candidate is a first plan: learned tau / delay apply (they finalize per plan otherwise)
         return self.step(action, _keep_state=True)
 
-    def step(self, action, _keep_state: bool = False):
+    def new_state_set(self):
+        """a private copy of the env state buffers (q, v, steps, done, ctx): an episode batch of its own next to the env's
+        (`reset_into` / `run_episode`; EpisodePipeline keeps one per batch in flight)"""
+        from types import SimpleNamespace
+        b = self._base
+        return SimpleNamespace(q=b.q.clone(), v=b.v.clone(), steps=b.steps.clone(), done=b.done.clone(), ctx=b.ctx.clone())
+
+    def reset_into(self, state):
+        """reset(seed=None) whose state lands in `state` (new_state_set()) instead of the env's own buffers: every env draws the
+        next context of its stream exactly as reset() would; returns the reset observation (device tensor)"""
+        if not self._fast_reset:
+            raise NotImplementedError("reset_into needs the device-side reset (context_sampler='device')")
+        self.traj_gen.reset()
+        return self._base.device_reset(None, obs_index=self._obs_index_np, time_aware=self._time_aware(), state=state)
+
+    def run_episode(self, action, state):
+        """step() for an env that plans once per episode, from `state` (reset_into) instead of the env's own buffers; the env
+        itself is left where it is.  Same returns as reset() + step()."""
+        if self.do_replanning or self.learn_sub_trajectories:
+            raise NotImplementedError("run_episode() is defined for envs that plan once per episode")
+        self.traj_gen.reset()
+        return self.step(action, _keep_state=True, _state=state)
+
+    def step(self, action, _keep_state: bool = False, _state=None):
         base = self._base
         params, as_numpy, scalar = self._prepare_params(action)
         self._set_plan(params)
@@ -481,7 +504,7 @@ class BlackBoxWrapper(Wrapper):
             seg_env = torch.where(valid, int(seg), 0).to(torch.int32)
             if self.traj_gen.n_steps_env is not None:
                 seg_env = torch.minimum(seg_env, self.traj_gen.n_steps_env)
-        self.launch(local, seg, replan_break, dbg, keep_state=_keep_state, trajectory=trajectory, seg_steps_env=seg_env)
+        self.launch(local, seg, replan_break, dbg, state=_state, keep_state=_keep_state, trajectory=trajectory, seg_steps_env=seg_env)
         if self.condition_on_desired and replan_break and not _keep_state:
             # the desired state is recorded on a BREAK only (black_box_wrapper.py:196-201): at a re-planning break every
             # live env breaks at the same step (the kernel wrote its row); a plan that simply runs out records nothing, and
@@ -500,7 +523,7 @@ class BlackBoxWrapper(Wrapper):
             infos["is_success"], infos["is_collided"] = success, collided
             infos["end_effector"] = self._info[:, 0:2]
             if getattr(base, "rew_fct", None) == "unbounded":        # hr_unbounded_reward.py:53-56
-                infos["joints"] = base.q.clone()
+                infos["joints"] = (base if _state is None else _state).q.clone()
         elif base.env_kind == _lib.ENV_SIMPLE_REACHER:
             infos["reward_dist"] = self._info[:, 0]
             infos["reward_ctrl"] = self._info[:, 1]

@@ -148,9 +148,11 @@ class BaseReacherEnv(Env):
         """(values[4], given[4]) of the constructor-fixed task context, laid out like `ctx`"""
         return [0.0] * 4, [0] * 4
 
-    def device_reset(self, seed=None, obs_index=None, time_aware=False, random_start=None, out=None, mask=None):
+    def device_reset(self, seed=None, obs_index=None, time_aware=False, random_start=None, out=None, mask=None, state=None):
         """fg_reset: one kernel samples the contexts (numpy-exact streams), resets the state buffers and writes the
-        observation columns `obs_index` of the reset state (default: the full step observation)."""
+        observation columns `obs_index` of the reset state (default: the full step observation).
+        `state`: object with q / v / steps / done / ctx device tensors that receive the reset state instead of the env's own
+        (several episode batches in flight, each with its own state: EpisodePipeline); the context streams advance all the same."""
         import ctypes as C
         B, n, dev = self.num_envs, self.n_links, self.device
         n_full = self.observation_space.shape[0] + (1 if time_aware else 0)
@@ -191,8 +193,9 @@ class BaseReacherEnv(Env):
         if mask is not None:       # partial reset: only envs with mask != 0 (their rows of `out` are rewritten, the rest kept)
             mask = mask.to(dev, torch.uint8).contiguous()
             io.mask = mask.data_ptr()
-        io.q, io.v, io.steps, io.done, io.ctx = (self.q.data_ptr(), self.v.data_ptr(), self.steps.data_ptr(),
-                                                 self.done.data_ptr(), self.ctx.data_ptr())
+        st = self if state is None else state
+        io.q, io.v, io.steps, io.done, io.ctx = (st.q.data_ptr(), st.v.data_ptr(), st.steps.data_ptr(),
+                                                 st.done.data_ptr(), st.ctx.data_ptr())
         obs = out if out is not None else torch.empty(B, len(idx), dtype=torch.float32, device=dev)
         io.obs = obs.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream

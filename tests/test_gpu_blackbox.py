@@ -289,8 +289,8 @@ def test_graphed_episode_replays_the_eager_episode(fg):
         assert torch.equal(term, e_term.cpu())
 
 
-@pytest.mark.parametrize("slots", [2, 3, 4])
-def test_episode_pipeline_equals_sequential_steps(fg, slots):
+@pytest.mark.parametrize("slots,graphs", [(2, False), (3, False), (4, False), (2, True), (3, True)])
+def test_episode_pipeline_equals_sequential_steps(fg, slots, graphs):
     """EpisodePipeline (2 - 4 batches in flight, H2D / rollout / D2H on their own streams) returns, batch for batch, what
     sequential reset() / step() calls return — including each env's context stream advancing once per batch"""
     import torch
@@ -302,7 +302,7 @@ def test_episode_pipeline_equals_sequential_steps(fg, slots):
     if slots > 2:
         with pytest.raises(ValueError):
             fg.EpisodePipeline(seq, slots=slots)          # two result sets only
-    pipe = fg.EpisodePipeline(piped, slots=slots)
+    pipe = fg.EpisodePipeline(piped, slots=slots, graphs=graphs)
     gen = torch.Generator().manual_seed(1)
     pops = [0.5 * torch.randn(B, 25, generator=gen) for _ in range(7)]
     want = []

@@ -17,11 +17,12 @@ dev = torch.device("cuda", lr)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 B, K = 65536, int(os.environ.get("STEPS", "300"))
-for slots in (2, 3, 4, 6):
+GRAPHS = os.environ.get("GRAPHS", "0") == "1"
+for slots in (2, 3, 4):
     env = fancy_gym.make("fancy_ProMP/HoleReacher-v0", num_envs=B, device=dev, context_sampler="device",
                          mp_config_override={"black_box_kwargs": {"result_sets": slots}})
     env.reset(seed=rank)
-    pipe = fancy_gym.EpisodePipeline(env, slots=slots)
+    pipe = fancy_gym.EpisodePipeline(env, slots=slots, graphs=GRAPHS)
     for hp in pipe.host_params:
         hp.copy_(0.25 * torch.randn(hp.shape))
 
@@ -50,7 +51,7 @@ for slots in (2, 3, 4, 6):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n)
     if rank == 0:
-        print(f"slots {slots}: {1e3 * float(t) / K:.4f} ms per step (max over {world} ranks), {float(n) / float(t):.3e} env-steps/s", flush=True)
+        print(f"graphs {int(GRAPHS)} slots {slots}: {1e3 * float(t) / K:.4f} ms per step (max over {world} ranks), {float(n) / float(t):.3e} env-steps/s", flush=True)
     env.close()
 if world > 1:
     dist.destroy_process_group()
