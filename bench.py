@@ -10,17 +10,19 @@ synthetic random MP parameters (sigma * N(0,1), torch Philox) and random task co
 
 Prints ONE JSON line (see README / DESIGN.md "Measurement" for the keys):
   value            whole-job env-steps/s with inputs resident in HBM (device-timed, max over ranks)
-  e2e              the same metric through the public API from pinned HOST buffers, per step reset() + H2D of that step's
-                   parameters + step() + D2H of its returns / lengths / flags inside the timed region, two batches in flight
-                   (fancy_gym_b200.EpisodePipeline: copies overlap the neighbouring rollouts); e2e_sync = the same calls with
-                   one batch at a time (the host waits for each batch before the next H2D)
+  e2e              the same metric through the public API from pinned HOST buffers, per step reset + H2D of that step's
+                   parameters + rollout + D2H of its returns / lengths / flags inside the timed region, four batches in flight
+                   (fancy_gym_b200.EpisodePipeline: every batch with its own env state and compute stream, replayed as CUDA
+                   graphs; copies and consecutive rollouts overlap); e2e_sync = reset() + step() with one batch at a time
+                   (the host waits for each batch before the next H2D)
   roofline         fused rollout kernel: algorithmic ops (4356 per HoleReacher/ProMP env step)
                    / measured kernel time, against the FP32 FFMA peak measured in the same run (fg_ffma_probe)
   roofline_trajgen trajectory-only kernel (fg_trajgen): algorithmic bytes (8 B per (t, dof)) / time vs measured HBM GB/s
   cpu_baseline     the oracle port of the reference's CPU path on this box's host cores (rank 0, N=1, bounded sample):
                    one env per process like the reference; the numpy-vectorised port is reported as an extra
 Multi-GPU (torchrun, one rank per GPU): the env batch is sharded, no data-path collective; per-step returns /
-lengths / flags are all-gathered over NCCL inside the timed region ("scaling": "weak").
+lengths / flags reach every rank inside the timed region — stored by the rollout kernel itself into peer-mapped gather buffers
+over NVLink (FG_BENCH_EXCHANGE=nccl: an overlapped ncclAllGather instead) ("scaling": "weak").
 """
 import argparse
 import json
