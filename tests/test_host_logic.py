@@ -353,3 +353,39 @@ def test_ragged_plans_need_a_finite_tau_bound():
     tg.set_params(p)
     with pytest.raises(ValueError, match="tau_bound"):
         tg.set_duration(None, 0.01)
+
+
+def test_rbf_recurrence_error_stays_far_inside_the_tie_margin():
+    """fg_device.cuh RbfRec (restated in numpy): normalised RBFs at a linear phase by phi_{k+1} = phi_k * r_k with a geometric
+    ratio — the float64 values stay within a few hundred ulps of the direct evaluation, the kernels fall back to the direct
+    evaluation within 2**12 ulps of a float32 rounding boundary: the float32 basis cannot change."""
+    import numpy as np
+    from fancy_gym_b200.mp.phase_gn import LinearPhaseGenerator
+    from fancy_gym_b200.mp.basis_gn import ZeroPaddingNormalizedRBFBasisGenerator as Z
+    for kw in (dict(num_basis=5, num_basis_zero_start=1), dict(num_basis=5, num_basis_zero_start=0), dict(num_basis=7, num_basis_zero_start=1)):
+        bg = Z(LinearPhaseGenerator(tau=2.0, delay=0.0, learn_tau=True, learn_delay=True), basis_bandwidth_factor=3.0, **kw)
+        cen, bw = np.asarray(bg.centers_p, np.float64), np.asarray(bg.bandwidth, np.float64)
+        n = cen.size
+        L = np.longdouble
+        A = -(L(bw[1:]) - L(bw[:-1])) / 2
+        Bc = L(bw[1:]) * L(cen[1:]) - L(bw[:-1]) * L(cen[:-1])
+        C = -(L(bw[1:]) * L(cen[1:]) ** 2 - L(bw[:-1]) * L(cen[:-1]) ** 2) / 2
+        assert abs(A[0]) < 1e-9 and np.all(np.abs(np.diff(A)) + np.abs(np.diff(Bc)) < 1e-9)      # what the host checks
+        q = np.exp(np.diff(C)).astype(np.float64)
+        da, db = np.diff(A).astype(np.float64), np.diff(Bc).astype(np.float64)
+        a0, b0, c0 = float(A[0]), float(Bc[0]), float(C[0])
+        p = np.float32(np.random.default_rng(0).random(200_000)).astype(np.float64)              # the phase is a float32 value
+        direct = np.exp(-((p[:, None] - cen) ** 2 * bw) / 2)
+        phi = np.empty_like(direct)
+        phi[:, 0] = direct[:, 0]
+        r = np.exp(b0 * p + c0)
+        r = r + r * (a0 * p * p)
+        for k in range(n - 1):
+            phi[:, k + 1] = phi[:, k] * r
+            if k + 2 < n:
+                rq = r * q[k]
+                r = rq + rq * ((da[k] * p + db[k]) * p)
+        direct /= direct.sum(1, keepdims=True)
+        phi /= phi.sum(1, keepdims=True)
+        rel = np.abs(phi - direct) / direct
+        assert rel.max() < 2.0 ** -40 / 8, rel.max()          # margin of the fall-back: 2**12 ulps = 2**-40 relative
